@@ -1,0 +1,86 @@
+/*
+ * drmrender.h -- C ABI of libdrmrender.so: B200 (sm_100a) implementation of DRMNet's data-parallel rendering hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain device pointers and sizes, never
+ * throws or aborts across the ABI, never calls cudaDeviceSynchronize, enqueues all work on the stream it is given and
+ * returns 0 on success or a negative DRM_E* code (message via drm_last_error(), thread-local).
+ * The caller owns every buffer including the workspace (query the size first); the library keeps no pointer after
+ * the call returns.  There is no CPU fallback: without a CUDA device every compute entry returns DRM_ECUDA.
+ *
+ * Reference interfaces replaced (paths relative to the DRMNet repository):
+ *   drm_render_refmaps      <- MitsubaRefMapRenderer.rendering()         utils/mitsuba3_utils.py:411-430 (-> :365-409, :217-246)
+ *                              and the per-render Python loops that call it  models/drmnet.py:561-569, :680-691
+ *   drm_img2refmap          <- refmap_mask_make()                        utils/img2refmap.py:6-37
+ *                              (+ xyz2thetaphi as called there             utils/transform.py:55-89)
+ */
+#ifndef DRMRENDER_H
+#define DRMRENDER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRM_VERSION 100 /* major*10000 + minor*100 + patch */
+
+enum {
+    DRM_OK = 0,
+    DRM_EINVAL = -1, /* bad argument (null pointer, non-positive size, unsupported value) */
+    DRM_EWORKSPACE = -2, /* workspace missing or too small */
+    DRM_ECUDA = -3, /* CUDA runtime / driver error, or no device */
+    DRM_EUNSUPPORTED = -4 /* valid request this build cannot serve */
+};
+
+int drm_version(void);
+const char* drm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reflectance-map forward render.
+ *
+ *   env        [B, He, We, 3] fp32 RGB lat-long radiance, row 0 = zenith (+Y), u = atan2(x,-z)/2pi (device)
+ *   env_index  [N] int32: which envmap render k uses (device)
+ *   z6         [N, 6] fp32: metallic, base R, base G, base B, roughness, specular -- clipped to [0,1] by the kernel
+ *              (utils/mitsuba3_utils.py:237-242); unnamed parameters carry the scene defaults 0,0,0,0,0,1 (:348-361)
+ *   view3      [N, 3] fp32 camera position (any positive length; the sensor looks at the origin, up = +Y, :235-236)
+ *   flip       [N] uint8 (may be NULL = no flip): mirrors the refmap columns (:38-40)
+ *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117); 1..16
+ *   alpha_min  lower clamp of the GGX alpha = roughness^2; <= 0 selects max(1e-3, 0.75*pi/He)
+ *   channel_first  0: out [N, res, res, 3];  1: out [N, 3, res, res]   (:196-198)
+ *   out        fp32 (device)
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t drm_render_workspace_bytes(int N, int B, int He, int We, int res, int footprint_S);
+
+int drm_render_refmaps(const float* env, int B, int He, int We,
+                       const int32_t* env_index, const float* z6, const float* view3, const uint8_t* flip,
+                       int N, int res, int footprint_S, float alpha_min, int channel_first,
+                       float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Image -> refmap scatter, batched over B images through `offsets`.
+ *
+ *   colors     [total_n, C] fp32, C in 1..4 (device)
+ *   normals_or_thetaphi  [total_n, 3] fp32 normals, or [total_n, 2] fp32 (theta, phi) when input_is_thetaphi != 0
+ *   offsets    [B + 1] int64, image b owns rows offsets[b] .. offsets[b+1]-1 (device)
+ *   thr        window half-width in radians (compared in fp32, utils/img2refmap.py:26-27)
+ *   min_points cells with fewer members are empty (:28)
+ *   reduce_mode 0 = lower median by channel sum (the reference, :30-34), 1 = mean in ascending pixel order (additive)
+ *   refmap     [B, res, res, C] fp32, zeros where empty;  refmask [B, res, res] uint8 (0/1)
+ *   counts     [B, res, res] int32 members per cell (may be NULL);  sel_index [B, res, res] int32 image-local index
+ *              of the selected pixel, -1 where empty or in mean mode (may be NULL)
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t drm_img2refmap_workspace_bytes(int64_t total_n, int B, int res, float thr);
+
+int drm_img2refmap(const float* colors, const float* normals_or_thetaphi, int input_is_thetaphi,
+                   const int64_t* offsets, int64_t total_n, int B, int C, int res, float thr, int min_points,
+                   int reduce_mode, float* refmap, uint8_t* refmask, int32_t* counts, int32_t* sel_index,
+                   void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* angles only: [n,3] normals -> [n,2] (theta, phi), the arithmetic of utils/transform.py:84-89 at img2refmap.py:20 */
+int drm_normals_to_thetaphi(const float* normals, int64_t n, float* thetaphi, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRMRENDER_H */

@@ -1,0 +1,187 @@
+/*
+ * CPU oracle for the reflectance-map forward render.  TEST INFRASTRUCTURE ONLY (fp64, plain C + OpenMP).
+ *
+ * PARITY UNPINNED: the reference delegates this arithmetic to Mitsuba 3 (v3.3.0 per
+ * environment/drmnet_release.def:54; `principled` BSDF, `envmap` emitter, `direct` integrator) which is not
+ * vendored under /root/reference, not installed here, and whose output is a 256-spp Monte-Carlo estimate passed
+ * through the OptiX AI denoiser.  This file restates the DETERMINISTIC LIMIT of that estimator from the scene the
+ * reference builds, and is pinned only by known-answer tests (white furnace, mirror limit against the reference's
+ * own torch renderer utils/transform.py:201-242, linearity, azimuth equivariance, flip symmetry, energy bounds).
+ *
+ * What is followed, with reference file:line
+ *   sensor geometry      utils/mitsuba3_utils.py:36-57     film sample (sx,sy) -> normal  n = sin(t)cos(p) left + cos(t) up' + sin(t)sin(p) v,
+ *                                                           t = pi*sy, p = pi*sx; `flip` negates the left component (:38-40)
+ *   camera frame         utils/mitsuba3_utils.py:115,235-236  look_at(origin = 1.1 v/|v|, target 0, up (0,1,0)):
+ *                                                           fwd = -v, left = normalize(up x fwd), up' = fwd x left
+ *   pixel filter         utils/mitsuba3_utils.py:116-117   box filter + stratified sampler -> uniform average over the (t,p) cell;
+ *                                                           here an S x S Gauss-Legendre rule over the cell
+ *   BSDF                 utils/mitsuba3_utils.py:345-361   `principled`, defaults base_color 0, metallic 0, specular 1, roughness 0, all else 0;
+ *                        utils/mitsuba3_utils.py:237-242   per-call overrides, each clipped to [0,1] (done by the caller of this file)
+ *   emitter              utils/mitsuba3_utils.py:112,233   lat-long radiance map, convention of utils/transform.py:207-209,230-233
+ *   integrator           utils/mitsuba3_utils.py:343       `direct`: convex sphere, emitter only -> single hemispherical integral
+ *
+ * Principled BSDF terms (Mitsuba 3 src/bsdfs/principled.cpp + principledhelpers.h, recalled -- see DESIGN.md):
+ *   alpha = max(alpha_min, roughness^2)       (Mitsuba: alpha_min = 1e-3)
+ *   eta   = 2 / (1 - sqrt(0.08 specular)) - 1
+ *   h = normalize(v + d);  D = 1 / (pi alpha^2 (cos^2 th + sin^2 th / alpha^2)^2)
+ *   G = G1(n.v) G1(n.d),   G1(c) = 2 / (1 + sqrt(1 + alpha^2 (1 - c^2) / c^2))
+ *   F_c = (1 - m) F_dielectric(v.h, eta) + m (c_c + (1 - c_c)(1 - v.h)^5)
+ *   spec_c = F_c D G / (4 n.v)
+ *   Fi = (1 - n.v)^5, Fo = (1 - n.d)^5, Rr = 2 roughness (h.d)^2
+ *   diff_c = (1 - m) (n.d) c_c / pi [ (1 - Fi/2)(1 - Fo/2) + Rr (Fo + Fi + Fo Fi (Rr - 1)) ]
+ *   value = spec + diff  (already includes the cosine), zero unless n.v > 0 and n.d > 0
+ *
+ * The emitter is given as a list of point masses ("records"): unit direction + radiance * solid angle, so the
+ * same routine evaluates the texel-centre quadrature of the full-resolution map and any coarser or finer level.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static double fresnel_dielectric(double cos_i, double eta) {
+    /* unpolarised Fresnel reflectance, outside incidence (cos_i >= 0, eta >= 1) */
+    double eta_ti = 1.0 / eta;
+    double ct2 = 1.0 - eta_ti * eta_ti * (1.0 - cos_i * cos_i);
+    if (ct2 <= 0.0) return 1.0;
+    double ct = sqrt(ct2);
+    double a_s = (cos_i - eta * ct) / (cos_i + eta * ct);
+    double a_p = (ct - eta * cos_i) / (ct + eta * cos_i);
+    return 0.5 * (a_s * a_s + a_p * a_p);
+}
+
+static double schlick_weight(double c) {
+    double m = 1.0 - c;
+    if (m < 0.0) m = 0.0;
+    if (m > 1.0) m = 1.0;
+    return (m * m) * (m * m) * m;
+}
+
+static double smith_g1(double c, double alpha) {
+    if (c <= 0.0) return 0.0;
+    double t2 = alpha * alpha * (1.0 - c * c) / (c * c);
+    if (t2 <= 0.0) return 1.0;
+    return 2.0 / (1.0 + sqrt(1.0 + t2));
+}
+
+/* camera frame of look_at(origin = v, target = 0, up = (0,1,0)) */
+static void camera_frame(const double* view, double* vhat, double* left, double* upp) {
+    double len = sqrt(view[0] * view[0] + view[1] * view[1] + view[2] * view[2]);
+    for (int k = 0; k < 3; ++k) vhat[k] = view[k] / len;
+    double fwd[3] = {-vhat[0], -vhat[1], -vhat[2]};
+    /* left = normalize(up x fwd), up = (0,1,0) */
+    double l[3] = {1.0 * fwd[2] - 0.0 * fwd[1], 0.0 * fwd[0] - 0.0 * fwd[2], 0.0 * fwd[1] - 1.0 * fwd[0]};
+    double ll = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int k = 0; k < 3; ++k) left[k] = l[k] / ll;
+    /* up' = fwd x left */
+    upp[0] = fwd[1] * left[2] - fwd[2] * left[1];
+    upp[1] = fwd[2] * left[0] - fwd[0] * left[2];
+    upp[2] = fwd[0] * left[1] - fwd[1] * left[0];
+}
+
+/*
+ * z6 = [metallic, base R, base G, base B, roughness, specular] (already clipped to [0,1]).
+ * gl_x / gl_w: S Gauss-Legendre nodes on [-1,1] and weights normalised to sum 1.
+ * terms: bit 0 = specular, bit 1 = diffuse.
+ * out: [res, res, 3] doubles.
+ */
+int drm_oracle_render_records(const double* rec_dir, const double* rec_E, long T,
+                              const double* z6, const double* view3, int flip,
+                              int res, int S, const double* gl_x, const double* gl_w,
+                              double alpha_min, int terms, double* out) {
+    const double m = z6[0], rough = z6[4], specular = z6[5];
+    const double base[3] = {z6[1], z6[2], z6[3]};
+    double alpha = rough * rough;
+    if (alpha < alpha_min) alpha = alpha_min;
+    const double eta = 2.0 / (1.0 - sqrt(0.08 * specular)) - 1.0;
+    double vhat[3], left[3], upp[3];
+    camera_frame(view3, vhat, left, upp);
+
+    /* per-record, pixel-independent terms */
+    double* pre = (double*)malloc(sizeof(double) * (size_t)T * 6);
+    if (!pre) return -1;
+    for (long t = 0; t < T; ++t) {
+        const double* d = rec_dir + 3 * t;
+        double vd = vhat[0] * d[0] + vhat[1] * d[1] + vhat[2] * d[2];
+        double len2 = 2.0 + 2.0 * vd; /* |v + d|^2 */
+        double inv_len = len2 > 1e-30 ? 1.0 / sqrt(len2) : 0.0;
+        double vh = (1.0 + vd) * inv_len; /* v.h = d.h */
+        double Fd = fresnel_dielectric(vh, eta);
+        double sw = schlick_weight(vh);
+        pre[6 * t + 0] = inv_len;
+        pre[6 * t + 1] = vh;
+        for (int c = 0; c < 3; ++c)
+            pre[6 * t + 2 + c] = (1.0 - m) * Fd + m * (base[c] + (1.0 - base[c]) * sw);
+        pre[6 * t + 5] = 0.0;
+    }
+
+    const double cell = M_PI / res;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int pix = 0; pix < res * res; ++pix) {
+        int i = pix / res, j = pix % res;
+        double acc[3] = {0, 0, 0};
+        for (int a = 0; a < S; ++a)
+            for (int b = 0; b < S; ++b) {
+                double th = (i + 0.5 + 0.5 * gl_x[a]) * cell;
+                double ph = (j + 0.5 + 0.5 * gl_x[b]) * cell;
+                double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
+                double lx = flip ? -st * cp : st * cp;
+                double n[3];
+                for (int k = 0; k < 3; ++k) n[k] = lx * left[k] + ct * upp[k] + st * sp * vhat[k];
+                double nv = n[0] * vhat[0] + n[1] * vhat[1] + n[2] * vhat[2];
+                if (nv <= 0.0) continue;
+                double g1v = smith_g1(nv, alpha);
+                double Fi = schlick_weight(nv);
+                double s_acc[3] = {0, 0, 0}, d_acc[3] = {0, 0, 0};
+                for (long t = 0; t < T; ++t) {
+                    const double* d = rec_dir + 3 * t;
+                    double nd = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+                    if (nd <= 0.0) continue;
+                    const double* p = pre + 6 * t;
+                    const double* E = rec_E + 3 * t;
+                    if (terms & 1) {
+                        double nh = (nv + nd) * p[0];
+                        double c2 = nh * nh;
+                        double q = c2 + (1.0 - c2) / (alpha * alpha);
+                        double D = 1.0 / (M_PI * alpha * alpha * q * q);
+                        if (D * nh <= 1e-20) D = 0.0;
+                        double w = D * g1v * smith_g1(nd, alpha) / (4.0 * nv);
+                        s_acc[0] += w * p[2] * E[0];
+                        s_acc[1] += w * p[3] * E[1];
+                        s_acc[2] += w * p[4] * E[2];
+                    }
+                    if (terms & 2) {
+                        double Fo = schlick_weight(nd);
+                        double Rr = 2.0 * rough * p[1] * p[1];
+                        double w = nd * ((1.0 - 0.5 * Fi) * (1.0 - 0.5 * Fo) + Rr * (Fo + Fi + Fo * Fi * (Rr - 1.0)));
+                        d_acc[0] += w * E[0];
+                        d_acc[1] += w * E[1];
+                        d_acc[2] += w * E[2];
+                    }
+                }
+                double wq = gl_w[a] * gl_w[b];
+                for (int c = 0; c < 3; ++c)
+                    acc[c] += wq * (s_acc[c] + (1.0 - m) * base[c] / M_PI * d_acc[c]);
+            }
+        out[3 * pix + 0] = acc[0];
+        out[3 * pix + 1] = acc[1];
+        out[3 * pix + 2] = acc[2];
+    }
+    free(pre);
+    return 0;
+}
+
+int drm_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/drmrender.h declares; argument validation
+and workspace queries work on the host.  No compute is launched here."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+from drmnet_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not _lib.SO_PATH.exists():
+        _lib.build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    header = (ROOT / "include" / "drmrender.h").read_text()
+    declared = sorted(set(re.findall(r"\b(drm_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in drmrender.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_version_and_error_string(lib):
+    assert lib.drm_version() == 100
+    assert isinstance(lib.drm_last_error(), bytes)
+
+
+def test_workspace_queries(lib):
+    assert lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1) > 0
+    assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 1) > lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1)
+    assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 17) == 0
+    assert lib.drm_render_workspace_bytes(0, 1, 1000, 2000, 128, 1) == 0
+    a = lib.drm_img2refmap_workspace_bytes(27774, 1, 128, 3.14159 / 256)
+    b = lib.drm_img2refmap_workspace_bytes(27774, 1, 128, 3.14159 / 64)
+    assert 0 < a < b
+    assert lib.drm_img2refmap_workspace_bytes(-1, 1, 128, 0.1) == 0
+
+
+def test_argument_validation_without_a_device(lib):
+    rc = lib.drm_render_refmaps(None, 1, 8, 16, None, None, None, None, 1, 8, 1, 0.0, 0, None, None, 0, None)
+    assert rc == _lib.DRM_EINVAL and b"null" in lib.drm_last_error()
+    rc = lib.drm_img2refmap(None, None, 0, None, 10, 1, 3, 16, 0.1, 0, 0, None, None, None, None, None, 0, None)
+    assert rc == _lib.DRM_EINVAL
+    rc = lib.drm_img2refmap(None, None, 0, None, 10, 1, 7, 16, 0.1, 0, 0, None, None, None, None, None, 0, None)
+    assert rc == _lib.DRM_EINVAL and b"C=7" in lib.drm_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+
+
+def test_python_wrappers_refuse_cpu_tensors():
+    import torch
+    from drmnet_b200.img2refmap import refmap_mask_make
+    from drmnet_b200.renderer import render_batch
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        refmap_mask_make(torch.ones(4, 3), torch.ones(4, 3), 16, 0.1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        render_batch(torch.ones(1, 8, 16, 3), torch.ones(1, 6), torch.ones(1, 3))
