@@ -40,6 +40,7 @@ def lib() -> ctypes.CDLL:
     vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
     L.drm_version.restype = i32
     L.drm_last_error.restype = ctypes.c_char_p
+    L.drm_launch_count.restype = i64
     L.drm_render_workspace_bytes.restype = sz
     L.drm_render_workspace_bytes.argtypes = [i32] * 6
     L.drm_render_refmaps.restype = i32
@@ -62,5 +63,5 @@ def check(code: int) -> None:
         raise DrmError(code, msg)
 
 
-EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_render_workspace_bytes", "drm_render_refmaps",
+EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_launch_count", "drm_render_workspace_bytes", "drm_render_refmaps",
                     "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_normals_to_thetaphi"]

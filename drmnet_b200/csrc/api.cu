@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+long long launches() { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 PFN_encodeTiled get_encode_tiled() {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -28,5 +32,7 @@ PFN_encodeTiled get_encode_tiled() {
 
 }  // namespace drm
 
+namespace drm { long long launches(); }
+extern "C" int64_t drm_launch_count(void) { return drm::launches(); }
 extern "C" int drm_version(void) { return DRM_VERSION; }
 extern "C" const char* drm_last_error(void) { return drm::g_error; }

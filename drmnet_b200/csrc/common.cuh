@@ -12,6 +12,7 @@
 namespace drm {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);
 
 #define DRM_CHECK_CUDA(expr)                                                                       \
     do {                                                                                           \

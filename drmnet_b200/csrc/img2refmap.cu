@@ -395,6 +395,7 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
         i2r_select<<<(unsigned)blocks, 256, 0, st>>>(a, M);
     }
     DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(total_n > 0 ? 6 : 4);
     return DRM_OK;
 }
 

@@ -297,9 +297,9 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 const float x = h.w * nh - nv[r];                     // n.d = |v+d| n.h - n.v
                 const float sin2 = u2 * (1.f - 0.25f * u2);           // 1 - (n.h)^2
                 const float q = 1.f + sin2 * rc.inv_a2m1;             // cos^2 + sin^2 / alpha^2
-                const float sq = fast_sqrt(x * x * rc.one_m_a2 + rc.alpha2);
-                const float xc = fmaxf(x, 0.f);
-                const float ws = xc * fast_rcp(q * q * (x + sq));     // D G1(n.d) up to per-sub-normal constants
+                const float xc = fmaxf(x, 0.f);                       // below the horizon: weight 0, denominator > 0
+                const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
+                const float ws = xc * fast_rcp(q * q * (xc + sq));    // D G1(n.d) up to per-sub-normal constants
                 acc[r][0] += ws * s.y;
                 acc[r][1] += ws * s.z;
                 acc[r][2] += ws * s.w;
@@ -463,7 +463,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         set_error("render: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
         return DRM_EWORKSPACE;
     }
-    if (!(alpha_min > 0.f)) alpha_min = fmaxf(1e-3f, (float)(0.75 * M_PI / He));
+    if (!(alpha_min > 0.f)) alpha_min = fmaxf(1e-3f, (float)(1.25 * M_PI / He));
 
     GatherArgs g{};
     g.env = env; g.rc = w.rc; g.sin_t = w.sin_t; g.cos_t = w.cos_t; g.sin_p = w.sin_p; g.cos_p = w.cos_p;
@@ -516,5 +516,6 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         render_reduce_splits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.partial, out, N, res, p.splits, channel_first);
     }
     DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(4 + (p.splits > 1 ? 1 : 0));
     return DRM_OK;
 }

@@ -55,10 +55,11 @@ def auto_footprint(roughness: float, res: int = 128) -> int:
 
 def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor, *,
                  env_index: Optional[torch.Tensor] = None, flip: Optional[torch.Tensor] = None,
-                 brdf_param_names: Optional[Sequence[str]] = None, res: int = 128, footprint_S: int = 1,
+                 brdf_param_names: Optional[Sequence[str]] = None, res: int = 128, footprint_S=1,
                  alpha_min: float = 0.0, channel_first: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """N renders in one launch.  envmaps [B,He,We,3] fp32 CUDA; z [N,P]; view_from [N,3]; env_index [N] int (default
-    arange, needs N == B); flip [N] bool.  Returns [N,3,res,res] (or [N,res,res,3])."""
+    arange, needs N == B); flip [N] bool; footprint_S an int, one int per render, or None (chosen per render from its
+    roughness by ``auto_footprint``).  Returns [N,3,res,res] (or [N,res,res,3])."""
     if not (isinstance(envmaps, torch.Tensor) and envmaps.is_cuda):
         raise RuntimeError("envmaps must be a CUDA tensor: drmnet_b200 has no CPU path")
     if envmaps.dim() != 4 or envmaps.shape[-1] != 3:
@@ -84,32 +85,56 @@ def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor
     view_from = view_from.contiguous()
     if view_from.shape[0] != N:
         raise ValueError("view_from must be [N,3]")
-    if env_index is None:
-        if N != B:
-            raise ValueError("env_index is required when N != B")
-        idx_ptr = None
-    else:
-        env_index = env_index.to(device=device, dtype=torch.int32).contiguous()
-        idx_ptr = env_index.data_ptr()
-    flip_ptr = None
-    if flip is not None:
-        flip = flip.to(device=device, dtype=torch.uint8).contiguous()
-        flip_ptr = flip.data_ptr()
     shape = (N, 3, res, res) if channel_first else (N, res, res, 3)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out has the wrong shape/dtype/layout")
-    L = _lib.lib()
-    with torch.cuda.device(device):
-        nbytes = L.drm_render_workspace_bytes(N, B, He, We, int(res), int(footprint_S))
+    if env_index is None:
+        if N != B:
+            raise ValueError("env_index is required when N != B")
+        env_index = torch.arange(N, dtype=torch.int32, device=device)
+    else:
+        env_index = env_index.to(device=device, dtype=torch.int32).contiguous()
+    if flip is not None:
+        flip = flip.to(device=device, dtype=torch.uint8).contiguous()
+
+    # footprint: one S for the whole batch, or one per render (None = from each render's roughness); renders are
+    # grouped by S and each group is one launch
+    if footprint_S is None:
+        rough = z6[:, 4].clip(0, 1).tolist()  # one small device-to-host read
+        per_render = [auto_footprint(r, res) for r in rough]
+    elif isinstance(footprint_S, int):
+        per_render = None
+    else:
+        per_render = [int(s) for s in (footprint_S.tolist() if isinstance(footprint_S, torch.Tensor) else footprint_S)]
+        if len(per_render) != N:
+            raise ValueError("footprint_S must be an int or have one entry per render")
+    if per_render is not None and len(set(per_render)) == 1:
+        footprint_S, per_render = per_render[0], None
+
+    def launch(S, zz, vv, ee, ff, oo):
+        n = zz.shape[0]
+        L = _lib.lib()
+        nbytes = L.drm_render_workspace_bytes(n, B, He, We, int(res), int(S))
         if nbytes == 0:
-            raise ValueError(f"render_batch: unsupported sizes N={N} B={B} He={He} We={We} res={res} S={footprint_S}")
+            raise ValueError(f"render_batch: unsupported sizes N={n} B={B} He={He} We={We} res={res} S={S}")
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _lib.check(L.drm_render_refmaps(envmaps.data_ptr(), B, He, We, idx_ptr, z6.data_ptr(), view_from.data_ptr(),
-                                        flip_ptr, N, int(res), int(footprint_S), float(alpha_min), int(channel_first),
-                                        out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                        torch.cuda.current_stream(device).cuda_stream))
+        _lib.check(L.drm_render_refmaps(envmaps.data_ptr(), B, He, We, ee.data_ptr(), zz.data_ptr(), vv.data_ptr(),
+                                        ff.data_ptr() if ff is not None else None, n, int(res), int(S),
+                                        float(alpha_min), int(channel_first), oo.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+
+    with torch.cuda.device(device):
+        if per_render is None:
+            launch(footprint_S, z6, view_from, env_index, flip, out)
+        else:
+            for S in sorted(set(per_render)):
+                ids = torch.tensor([i for i, s in enumerate(per_render) if s == S], device=device)
+                part = torch.empty((ids.numel(),) + shape[1:], dtype=torch.float32, device=device)
+                launch(S, z6[ids].contiguous(), view_from[ids].contiguous(), env_index[ids].contiguous(),
+                       flip[ids].contiguous() if flip is not None else None, part)
+                out.index_copy_(0, ids, part)
     return out
 
 
@@ -117,7 +142,7 @@ class B200RefMapRenderer:
     """Same interface as MitsubaRefMapRenderer (utils/mitsuba3_utils.py:317-339, 411-430).
 
     Extra keywords: ``footprint_S`` (Gauss-Legendre sub-normals per cell and axis; None = chosen from the roughness of
-    each call, which costs one device-to-host read of z) and ``alpha_min`` (None = max(1e-3, 0.75*pi/He)).  ``spp`` and
+    each call, which costs one device-to-host read of z) and ``alpha_min`` (None = max(1e-3, 1.25*pi/He)).  ``spp`` and
     ``denoise`` are kept as attributes because datasets derive cache paths from them
     (dataset/parametricrefmap.py:135-139) but the image is noise free and needs no denoiser.
     """

@@ -35,6 +35,8 @@ enum {
 
 int drm_version(void);
 const char* drm_last_error(void);
+/* process-wide count of kernels this library has launched so far (bench.py reports the per-step difference) */
+int64_t drm_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Reflectance-map forward render.
@@ -46,7 +48,7 @@ const char* drm_last_error(void);
  *   view3      [N, 3] fp32 camera position (any positive length; the sensor looks at the origin, up = +Y, :235-236)
  *   flip       [N] uint8 (may be NULL = no flip): mirrors the refmap columns (:38-40)
  *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117); 1..16
- *   alpha_min  lower clamp of the GGX alpha = roughness^2; <= 0 selects max(1e-3, 0.75*pi/He)
+ *   alpha_min  lower clamp of the GGX alpha = roughness^2; <= 0 selects max(1e-3, 1.25*pi/He)
  *   channel_first  0: out [N, res, res, 3];  1: out [N, 3, res, res]   (:196-198)
  *   out        fp32 (device)
  * ------------------------------------------------------------------------------------------------------------- */

@@ -83,8 +83,8 @@ def gauss_legendre(S: int):
 
 
 def default_alpha_min(He: int) -> float:
-    """Smallest GGX alpha the texel-centre quadrature of an He-row map resolves: max(1e-3, 0.75 * pi / He)."""
-    return max(1e-3, 0.75 * np.pi / He)
+    """Smallest GGX alpha the texel-centre quadrature of an He-row map resolves: max(1e-3, 1.25 * pi / He)."""
+    return max(1e-3, 1.25 * np.pi / He)
 
 
 def render_records(dirs, E, z6, view, res, S=1, flip=False, alpha_min=1e-3, terms=3) -> np.ndarray:

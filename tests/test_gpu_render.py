@@ -1,0 +1,151 @@
+"""GPU parity for the refmap render: CUDA path through the C-ABI against the fp64 oracle on the same seeded inputs.
+Tolerance: relative L2 <= 1e-4 per refmap (BASELINE.json north_star), fp32 kernel vs fp64 oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from drmnet_b200.renderer import B200RefMapRenderer, render_batch
+from drmnet_b200.synth import BRDF_PARAM_NAMES, Z0, sample_brdf, sample_view, schedule_point, synthetic_envmap
+from oracle.render_oracle import rel_l2, render_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def _render(envs, z, views, res, S, **kw):
+    out = render_batch(torch.as_tensor(np.asarray(envs)).to(DEV), torch.as_tensor(np.asarray(z), dtype=torch.float32),
+                       torch.as_tensor(np.asarray(views), dtype=torch.float32), res=res, footprint_S=S, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+Z_CASES = {
+    "z0_mirror": list(Z0),
+    "rough_dielectric": [0.0, 0.9, 0.5, 0.2, 0.7, 0.5],
+    "glossy_metal": [1.0, 0.95, 0.6, 0.3, 0.3, 1.0],
+    "mixed": [0.4, 0.3, 0.8, 0.6, 0.45, 0.8],
+    "random7": sample_brdf(7).tolist(),
+    "near_mirror_schedule": schedule_point(sample_brdf(11), 0.1)[2].tolist(),
+}
+VIEWS = [[0.0, 0.0, 1.1], [1.0, 0.0, 0.0], [math.sin(0.7), 0.0, math.cos(0.7)], [-0.5, 0.3, -0.8]]
+
+
+@pytest.mark.parametrize("zname", list(Z_CASES))
+@pytest.mark.parametrize("shape", [(64, 128), (250, 500)])
+def test_parity_small_maps(zname, shape):
+    """5 envmaps x 6 BRDFs x 4 views over the two map sizes (views and envmaps cycled), res 16/24, S = 2."""
+    He, We = shape
+    res = 16 if He == 64 else 24
+    z = Z_CASES[zname]
+    envs = [synthetic_envmap(He, We, seed=1000 + b) for b in range(5 if He == 64 else 2)]
+    views = [VIEWS[(b + len(zname)) % 4] for b in range(len(envs))]
+    ours = _render(np.stack(envs), [z] * len(envs), views, res, 2, channel_first=False)
+    for b, env in enumerate(envs):
+        ref = render_oracle(env, z, views[b], res, S=2)
+        assert rel_l2(ours[b], ref) <= TOL, (zname, shape, b, rel_l2(ours[b], ref))
+
+
+@pytest.mark.parametrize("S", [1, 3, 4, 8])
+def test_parity_footprints(S):
+    env = synthetic_envmap(64, 128, seed=21)
+    z = Z_CASES["glossy_metal"]
+    ours = _render(env[None], [z], [VIEWS[2]], 12, S, channel_first=False)[0]
+    assert rel_l2(ours, render_oracle(env, z, VIEWS[2], 12, S=S)) <= TOL
+
+
+def test_parity_non_tma_pitch_and_odd_sizes():
+    """We*12 bytes not a multiple of 16 -> plain-load staging; sizes that are not multiples of the 32-texel tile."""
+    env = synthetic_envmap(50, 101, seed=4)
+    z = Z_CASES["mixed"]
+    ours = _render(env[None], [z], [VIEWS[0]], 10, 2, channel_first=False)[0]
+    assert rel_l2(ours, render_oracle(env, z, VIEWS[0], 10, S=2)) <= TOL
+
+
+@pytest.mark.parametrize("zname", ["z0_mirror", "random7"])
+def test_parity_full_size_envmap(zname):
+    """BASELINE's 2000x1000 map; res 16 keeps the fp64 oracle at a few seconds (the texel sum is res independent)."""
+    env = synthetic_envmap(1000, 2000, seed=1001)
+    z = Z_CASES[zname]
+    ours = _render(env[None], [z], [VIEWS[2]], 16, 1, channel_first=False)[0]
+    assert rel_l2(ours, render_oracle(env, z, VIEWS[2], 16, S=1)) <= TOL
+
+
+def test_full_size_128_properties():
+    """BASELINE config[1] shape (2000x1000 -> 128x128): linearity, flip symmetry, azimuth equivariance, furnace."""
+    dev_env = synthetic_envmap(1000, 2000, seed=1002, device=DEV)
+    dev_env2 = synthetic_envmap(1000, 2000, seed=1003, device=DEV)
+    z = torch.tensor([Z_CASES["mixed"]])
+    v = torch.tensor([[0.0, 0.0, 1.0]])
+    a = render_batch(dev_env[None], z, v, res=128)
+    b = render_batch(dev_env2[None], z, v, res=128)
+    ab = render_batch((2.0 * dev_env + 0.5 * dev_env2)[None], z, v, res=128)
+    assert rel_l2(ab.cpu().numpy(), (2.0 * a + 0.5 * b).cpu().numpy()) < 2e-6
+    f = render_batch(dev_env[None], z, v, res=128, flip=torch.tensor([True]))
+    assert rel_l2(f.flip(-1).cpu().numpy(), a.cpu().numpy()) < 1e-6
+    # rolling the map by 250 of 2000 columns == rotating the camera by 45 degrees about +Y
+    ang = 2 * math.pi * 250 / 2000
+    v2 = torch.tensor([[math.sin(math.pi + ang) * 1.0, 0.0, -math.cos(math.pi + ang) * 1.0]])
+    r = render_batch(torch.roll(dev_env, 250, dims=1)[None], z, v2, res=128)
+    assert rel_l2(r.cpu().numpy(), a.cpu().numpy()) < 2e-5
+    # white furnace (basis_r0 of models/drmnet.py:328-347): 1 in the interior; toward the limb the reflected lobe is
+    # compressed below the texel pitch and the texel-centre quadrature of the canonical definition degrades
+    white = render_batch(torch.ones(1, 1000, 2000, 3, device=DEV), torch.tensor([list(Z0)]), v, res=128,
+                         footprint_S=2)[0]
+    assert (white[:, 32:-32, 32:-32] - 1).abs().max() < 2e-3
+    assert (white[:, 16:-16, 16:-16] - 1).abs().max() < 5e-2
+    assert a.shape == (1, 3, 128, 128) and torch.isfinite(a).all()
+
+
+def test_batch_env_index_layouts_and_splits():
+    """G renders sharing one envmap (models/drmnet.py:561-569 groups), channel-first vs channel-last, and the
+    split-texel path (N = 1) against the unsplit path (N large)."""
+    envs = np.stack([synthetic_envmap(64, 128, seed=s) for s in (31, 32)])
+    zs = [Z_CASES["z0_mirror"], Z_CASES["mixed"], Z_CASES["rough_dielectric"]] * 14  # N = 42 -> no splits
+    idx = torch.tensor([i % 2 for i in range(len(zs))], dtype=torch.int32)
+    views = [VIEWS[i % 4] for i in range(len(zs))]
+    cf = _render(envs, zs, views, 16, 1, env_index=idx, channel_first=True)
+    cl = _render(envs, zs, views, 16, 1, env_index=idx, channel_first=False)
+    assert np.array_equal(cf.transpose(0, 2, 3, 1), cl)
+    for i in (0, 1, 2, 5):
+        one = _render(envs[int(idx[i]):int(idx[i]) + 1], [zs[i]], [views[i]], 16, 1, channel_first=False)[0]  # splits
+        assert rel_l2(one, cl[i]) < 5e-6
+        assert rel_l2(cl[i], render_oracle(envs[int(idx[i])], zs[i], views[i], 16, S=1)) <= TOL
+
+
+def test_determinism():
+    env = synthetic_envmap(64, 128, seed=77)
+    outs = [_render(env[None], [Z_CASES["mixed"]], [VIEWS[3]], 16, 2) for _ in range(3)]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_dropin_class_statefulness_and_attributes():
+    """Same ctor kwargs/attributes as MitsubaRefMapRenderer (utils/mitsuba3_utils.py:318-339) and the 'None keeps the
+    last value' protocol used by models/drmnet.py:561-569."""
+    r = B200RefMapRenderer(refmap_res=16, spp=256, envmap_size=(64, 128), denoise="simple",
+                           brdf_param_names=BRDF_PARAM_NAMES, footprint_S=2)
+    assert (r.refmap_res, r.image_size, r.spp, r.envmap_size, r.denoise) == (16, (16, 16), 256, (64, 128), "simple")
+    env = torch.from_numpy(synthetic_envmap(64, 128, seed=8)).to(DEV)
+    z = torch.tensor(Z_CASES["mixed"])
+    view = torch.tensor(VIEWS[2])
+    a = r.rendering(z, BRDF_PARAM_NAMES, envmap=env, view_from=view, channel_first=True)
+    assert a.shape == (3, 16, 16) and a.is_cuda and a.dtype == torch.float32
+    b = r.rendering(z, None, channel_first=False)  # keeps envmap and view; names fall back to the ctor list
+    assert torch.equal(a.permute(1, 2, 0), b)
+    ref = render_oracle(env.cpu().numpy(), Z_CASES["mixed"], VIEWS[2], 16, S=2)
+    assert rel_l2(b.cpu().numpy(), ref) <= TOL
+    # unnamed parameters keep their last value in the persistent scene
+    c = r.rendering(torch.tensor([0.9]), ["roughness.value"])
+    z2 = list(Z_CASES["mixed"]); z2[4] = 0.9
+    assert rel_l2(c.cpu().numpy(), render_oracle(env.cpu().numpy(), z2, VIEWS[2], 16, S=2)) <= TOL
+    # new_scene renders with fresh BSDF defaults and does not disturb the persistent scene
+    d = r.rendering(torch.tensor([0.9]), ["roughness.value"], envmap=env, new_scene=True)
+    assert rel_l2(d.cpu().numpy(), render_oracle(env.cpu().numpy(), [0.9], [0, 0, 1.1], 16, S=2,
+                                                 names=["roughness.value"])) <= TOL
+    with pytest.raises(AssertionError):
+        r.rendering(z, BRDF_PARAM_NAMES, envmap=env[0])  # envmap must be 3-D (utils/mitsuba3_utils.py:424)
+    bad = env.clone(); bad[0, 0, 0] = float("nan")
+    with pytest.raises(AssertionError):
+        r.rendering(z, BRDF_PARAM_NAMES, envmap=bad)

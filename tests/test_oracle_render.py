@@ -36,13 +36,13 @@ def test_solid_angles_sum_to_4pi():
 
 @pytest.mark.parametrize("tag", ["v001", "v100", "vdiag"])
 def test_mirror_limit_matches_reference_envmap2mirmap(golden_mirmap, tag):
-    """K2: pins rows/cols/left-right, the envmap azimuth convention and the view frame.  The residual ~0.1 is the
+    """K2: pins rows/cols/left-right, the envmap azimuth convention and the view frame.  The residual ~0.15 is the
     GGX blur (alpha_min at He = 128) against the reference's box-filtered perfect mirror; any wrong convention
     (flip, transpose) gives > 0.8."""
     env, view, mir = golden_mirmap["env"], golden_mirmap[f"view_{tag}"], golden_mirmap[f"mirmap_{tag}"]
     r = render_oracle(env, Z0, view, 32, S=4)
     ok = rel_l2(r, mir)
-    assert ok < 0.15
+    assert ok < 0.2
     for wrong in (r[:, ::-1], r[::-1], r.transpose(1, 0, 2)):
         assert rel_l2(wrong, mir) > 4 * ok
 
@@ -96,5 +96,5 @@ def test_footprint_converges_to_cell_average():
 def test_gauss_legendre_and_alpha_min():
     x, w = gauss_legendre(4)
     assert abs(w.sum() - 1) < 1e-15 and abs((w * x ** 6).sum() - 1 / 7) < 1e-14
-    assert default_alpha_min(1000) == pytest.approx(0.75 * np.pi / 1000)
+    assert default_alpha_min(1000) == pytest.approx(1.25 * np.pi / 1000)
     assert default_alpha_min(100000) == 1e-3
