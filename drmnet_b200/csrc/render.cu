@@ -14,6 +14,8 @@
 // LDS.128).  The kernel is bound by the FP32/MUFU pipes (about 34 instructions per (sub-normal, texel) pair), not by
 // HBM: each envmap byte is reused by every sub-normal of the render out of L2.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -21,16 +23,19 @@ namespace drm {
 
 static constexpr int GATHER_THREADS = 256;
 static constexpr int SUBS_PER_THREAD = 4;
-static constexpr int SLOTS = GATHER_THREADS * SUBS_PER_THREAD;  // sub-normals per CTA
+static constexpr int SLOTS = GATHER_THREADS * SUBS_PER_THREAD;  // sub-normal slots per CTA
 static constexpr int TT = 32;                                   // texel tile edge
 static constexpr int TILE_TEXELS = TT * TT;
 static constexpr int RAW_FLOATS = TT * TT * 3;
 static constexpr int REC_FLOATS = 12;
+static constexpr int MAX_LEVELS = 5;      // footprint lattices 1,2,4,8,16 per axis
+static constexpr int MAX_LIST = 2048;     // texel tiles one CTA can schedule (plan splits larger maps)
 
 struct RenderConst {  // per render
     float vhat[3], left[3], upp[3];  // camera frame of look_at(v, 0, +Y); `left` carries the flip sign
     float m, rough, alpha2, inv_a2m1, one_m_a2, eta;
     float base[3], cdiff[3];
+    float thr[MAX_LEVELS];  // half-vector-space distance beyond which footprint level k is accurate enough
     int env, has_diffuse;
 };
 
@@ -44,8 +49,11 @@ struct GatherArgs {
     int tile_w, tile_h, tiles_x, tiles_y;
     int ttiles_x, ttiles_y, splits;
     int channel_first, use_tma, cull;
+    int nlev;                 // number of footprint levels used by this launch
+    int lev_S[MAX_LEVELS];    // lattice size per axis of level k (ascending; the last one is S)
+    int lev_tidx[MAX_LEVELS]; // log2(lev_S[k]): index into RenderConst::thr
     float domega_k, cell;
-    float gl_x[16], gl_w[16];
+    float gl_x[MAX_LEVELS][16], gl_w[MAX_LEVELS][16];
 };
 
 __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, float* cos_p, int He, int We) {
@@ -65,7 +73,8 @@ __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, f
 // clip z to [0,1] (mitsuba3_utils.py:239,242), derive the BSDF constants and the camera frame (:235-236)
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N,
-                                    int B, float alpha_min, RenderConst* __restrict__ rc) {
+                                    int B, float alpha_min, float cell, float level_scale,
+                                    RenderConst* __restrict__ rc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     RenderConst c;
@@ -79,6 +88,18 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
     c.inv_a2m1 = 1.f / c.alpha2 - 1.f;
     c.one_m_a2 = 1.f - c.alpha2;
     c.eta = 2.f / (1.f - sqrtf(0.08f * z[5])) - 1.f;
+    // Distance (angle between the cell's normal and the half vector, radians) beyond which a coarser footprint
+    // lattice integrates the GGX tail ~ (alpha^2 + d^2)^-2 over the cell accurately enough: the S-point
+    // Gauss-Legendre error ~ K_S (cell/d)^(2S) weighted by the tail mass (alpha/d)^2 is held near 1e-5.
+    {
+        const float ca = cell * alpha;
+        c.thr[0] = 21.0f * sqrtf(ca);                                  // 1 x 1
+        c.thr[1] = 7.5f * powf(cell, 2.f / 3.f) * powf(alpha, 1.f / 3.f);  // 2 x 2
+        c.thr[2] = 2.4f * powf(cell, 0.8f) * powf(alpha, 0.2f);        // 4 x 4
+        c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);  // 8 x 8
+        c.thr[4] = 0.f;                                                // 16 x 16
+        for (int i = 0; i < MAX_LEVELS - 1; ++i) c.thr[i] = level_scale * fmaxf(c.thr[i], 6.f * alpha);
+    }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     c.has_diffuse = (c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f) ? 1 : 0;
     float vx = view3[3 * k], vy = view3[3 * k + 1], vz = view3[3 * k + 2];
@@ -109,21 +130,37 @@ __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
     return 0.5f * (a_s * a_s + a_p * a_p);
 }
 
-// conservative visibility of a texel tile from a cone of normals: some n in the cone has n.d > 0 for some d in the tile
-__device__ __forceinline__ bool tile_visible(const GatherArgs& g, int tile, float ax, float ay, float az, float beta) {
+// Classify one texel tile for a CTA whose normals lie in the cone (axis a, radius beta):
+//   0      no normal of the cone sees any texel of the tile (n.d <= 0 everywhere): skipped
+//   1+k    footprint level k (0 = 1x1 lattice ... nlev-1 = full S x S lattice) chosen from the distance, in
+//          half-vector space, between the cone of normals and the tile's half vectors h = normalize(v + d)
+__device__ __forceinline__ int classify_tile(const GatherArgs& g, const float* __restrict__ vhat,
+                                             const float* __restrict__ thr, int tile, float ax, float ay, float az,
+                                             float beta) {
     const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
     const int r0 = ty * TT, r1 = min(r0 + TT, g.He), c0 = tx * TT, c1 = min(c0 + TT, g.We);
     const float dth = 0.5f * (r1 - r0) * (3.14159265f / g.He), dph = 0.5f * (c1 - c0) * (6.2831853f / g.We);
     const float thc = 0.5f * (r0 + r1) * (3.14159265f / g.He), phc = 0.5f * (c0 + c1) * (6.2831853f / g.We);
     float st, ct, sp, cp;
-    __sincosf(thc, &st, &ct);
-    __sincosf(phc, &sp, &cp);
-    // angular radius: meridian move + parallel move (arc on the parallel bounds the great-circle distance)
+    sincosf(thc, &st, &ct);
+    sincosf(phc, &sp, &cp);
+    // angular radius of the tile: meridian move + parallel move (the arc on the parallel bounds the great-circle one)
     const float gamma = dth + dph * fminf(1.f, st + dth);
-    const float spread = beta + gamma + 0.01f;
-    if (spread >= 1.5607963f) return true;
-    const float dot = ax * (st * sp) + ay * ct - az * (st * cp);
-    return dot > -__sinf(spread);
+    const float dx = st * sp, dy = ct, dz = -st * cp;
+    if (g.cull) {
+        const float spread = beta + gamma + 0.01f;
+        if (spread < 1.5607963f && ax * dx + ay * dy + az * dz <= -sinf(spread)) return 0;
+    }
+    if (g.nlev == 1) return 1;
+    const float hx = vhat[0] + dx, hy = vhat[1] + dy, hz = vhat[2] + dz;
+    const float len = sqrtf(hx * hx + hy * hy + hz * hz);
+    if (len - gamma < 0.05f) return g.nlev;  // d ~ -v: the d -> h map is singular, stay on the finest lattice
+    const float gamma_h = gamma / (len - gamma);  // |dh| <= |dd| / |v + d|
+    const float cosang = fminf(fmaxf((ax * hx + ay * hy + az * hz) / len, -1.f), 1.f);
+    const float dist = acosf(cosang) - beta - gamma_h;
+    for (int k = 0; k < g.nlev - 1; ++k)
+        if (dist >= thr[g.lev_tidx[k]]) return 1 + k;
+    return g.nlev;
 }
 
 template <bool HAS_DIFFUSE>
@@ -132,7 +169,11 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* raw0 = reinterpret_cast<float*>(smem_raw);
     float4* rec = reinterpret_cast<float4*>(smem_raw + 2 * RAW_FLOATS * sizeof(float));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float));
+    unsigned char* tail = smem_raw + 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                 // 2 mbarriers
+    int* scan_ws = reinterpret_cast<int*>(tail + 16);                     // 8 warp sums + level starts
+    uint16_t* list = reinterpret_cast<uint16_t*>(tail + 16 + 64);         // [MAX_LIST] tiles ordered by level
+    uint8_t* lvl = reinterpret_cast<uint8_t*>(tail + 16 + 64 + MAX_LIST * 2);  // [MAX_LIST]
 
     const int tid = threadIdx.x;
     const int k = blockIdx.y;
@@ -145,34 +186,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     const int S2 = g.S * g.S;
     const int npix = g.tile_w * g.tile_h;
 
-    // ---- my sub-normals --------------------------------------------------------------------------------------
-    float nx[SUBS_PER_THREAD], ny[SUBS_PER_THREAD], nz[SUBS_PER_THREAD], nv[SUBS_PER_THREAD];
-    float Fi[SUBS_PER_THREAD];
-    float wq[SUBS_PER_THREAD];
-#pragma unroll
-    for (int r = 0; r < SUBS_PER_THREAD; ++r) {
-        const int q = r * GATHER_THREADS + tid;
-        const int pl = q / S2, sub = q - pl * S2;
-        const int li = pl / g.tile_w, lj = pl - li * g.tile_w;
-        const int i = pi0 + li, j = pj0 + lj;
-        const int a = sub / g.S, b = sub - a * g.S;
-        const bool active = pl < npix && i < g.res && j < g.res;
-        const float th = ((float)i + 0.5f + 0.5f * g.gl_x[a]) * g.cell;
-        const float ph = ((float)j + 0.5f + 0.5f * g.gl_x[b]) * g.cell;
-        float st, ct, sp, cp;
-        sincosf(th, &st, &ct);
-        sincosf(ph, &sp, &cp);
-        const float lx = st * cp, lz = st * sp;
-        nx[r] = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
-        ny[r] = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
-        nz[r] = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
-        nv[r] = lz;  // n . v exactly, the frame is orthonormal
-        const float mm = fminf(fmaxf(1.f - lz, 0.f), 1.f);
-        Fi[r] = (mm * mm) * (mm * mm) * mm;
-        wq[r] = active ? g.gl_w[a] * g.gl_w[b] : 0.f;
-    }
-
-    // ---- cone of this CTA's normals for tile culling -----------------------------------------------------------
+    // ---- cone of this CTA's normals (cell corners included) ---------------------------------------------------------
     float ax, ay, az, beta;
     {
         const int i1 = min(pi0 + g.tile_h, g.res), j1 = min(pj0 + g.tile_w, g.res);
@@ -185,22 +199,8 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         ay = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
         az = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
         const float dth = 0.5f * (i1 - pi0) * g.cell, dph = 0.5f * (j1 - pj0) * g.cell;
-        beta = g.cull ? dth + dph * fminf(1.f, st + dth) : 10.f;
+        beta = dth + dph * fminf(1.f, st + dth);
     }
-
-    const int ntiles = g.ttiles_x * g.ttiles_y;
-    const int per = (ntiles + g.splits - 1) / g.splits;
-    const int tbeg = blockIdx.z * per, tend = min(tbeg + per, ntiles);
-    auto next_visible = [&](int t) {
-        while (t < tend && !tile_visible(g, t, ax, ay, az, beta)) ++t;
-        return t;
-    };
-
-    float tot[SUBS_PER_THREAD][6];
-#pragma unroll
-    for (int r = 0; r < SUBS_PER_THREAD; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) tot[r][c] = 0.f;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -208,25 +208,116 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         mbar_fence_init();
         if (g.use_tma) tma_prefetch_desc(&tmap);
     }
-    __syncthreads();
 
-    auto issue = [&](int tile, int stage) {
+    // ---- schedule: classify my texel tiles, then order them by footprint level (coarse first, tile order inside) ----
+    const int ntiles = g.ttiles_x * g.ttiles_y;
+    const int per = (ntiles + g.splits - 1) / g.splits;
+    const int tbeg = blockIdx.z * per, tend = min(tbeg + per, ntiles);
+    const int nmine = tend - tbeg;
+    for (int e = tid; e < nmine; e += GATHER_THREADS)
+        lvl[e] = (uint8_t)classify_tile(g, g.rc[k].vhat, g.rc[k].thr, tbeg + e, ax, ay, az, beta);
+    __syncthreads();
+    int nlist = 0;
+    {
+        constexpr int PER_T = MAX_LIST / GATHER_THREADS;
+        const int lane = tid & 31, w = tid >> 5;
+        for (int L = 1; L <= g.nlev; ++L) {
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < PER_T; ++u) {
+                const int e = tid * PER_T + u;
+                cnt += (e < nmine && lvl[e] == L);
+            }
+            int inc = cnt;
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) scan_ws[w] = inc;
+            __syncthreads();
+            int wpre = 0, total = 0;
+            for (int ww = 0; ww < GATHER_THREADS / 32; ++ww) {
+                const int v = scan_ws[ww];
+                if (ww < w) wpre += v;
+                total += v;
+            }
+            int pos = nlist + wpre + inc - cnt;
+#pragma unroll
+            for (int u = 0; u < PER_T; ++u) {
+                const int e = tid * PER_T + u;
+                if (e < nmine && lvl[e] == L) list[pos++] = (uint16_t)e;
+            }
+            if (tid == 0) scan_ws[8 + L] = nlist + total;  // end of level L in the list
+            nlist += total;
+            __syncthreads();
+        }
+    }
+
+    float tot[SUBS_PER_THREAD][6];
+#pragma unroll
+    for (int r = 0; r < SUBS_PER_THREAD; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tot[r][c] = 0.f;
+
+    auto issue = [&](int e, int stage) {
+        const int tile = tbeg + list[e];
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
         mbar_arrive_expect_tx(&bars[stage], RAW_FLOATS * sizeof(float));
         tma_load_3d(raw0 + stage * RAW_FLOATS, &tmap, &bars[stage], tx * TT * 3, ty * TT, rc.env);
     };
-
-    int cur = next_visible(tbeg);
-    int nxt = next_visible(cur + 1);
     if (g.use_tma && tid == 0) {
-        if (cur < tend) issue(cur, 0);
-        if (nxt < tend) issue(nxt, 1);
+        if (0 < nlist) issue(0, 0);
+        if (1 < nlist) issue(1, 1);
     }
 
-    for (int it = 0; cur < tend; ++it) {
+    // ---- per-level state of my 4 slots: lattice node, texel subset, normals -----------------------------------------
+    // slot q = r*256 + tid -> pixel q / S^2, sub = q % S^2.  At a level with an Sk x Sk lattice the S^2 slots of a
+    // pixel form Sk^2 groups of gk = (S/Sk)^2 slots: the group evaluates one lattice node, its gk slots split the tile's
+    // texels (t = u, u+gk, ...).  S^2 divides 256, so the 4 slots of a thread share node and subset.
+    float nx[SUBS_PER_THREAD], ny[SUBS_PER_THREAD], nz[SUBS_PER_THREAD], nv[SUBS_PER_THREAD];
+    float Fi[SUBS_PER_THREAD], mult[SUBS_PER_THREAD], wq[SUBS_PER_THREAD];
+    int cur_level = 0, level_end = 0, gk = 1, u0 = 0;
+    const bool hier = (GATHER_THREADS % S2) == 0;
+
+    for (int it = 0; it < nlist; ++it) {
+        if (it >= level_end) {
+            // next non-empty level
+            do { ++cur_level; level_end = scan_ws[8 + cur_level]; } while (it >= level_end);
+            const int Sk = g.lev_S[cur_level - 1];
+            const int ratio = g.S / Sk;
+            gk = hier ? ratio * ratio : 1;
+#pragma unroll
+            for (int r = 0; r < SUBS_PER_THREAD; ++r) {
+                const int q = r * GATHER_THREADS + tid;
+                const int pl = q / S2, sub = q - pl * S2;
+                const int li = pl / g.tile_w, lj = pl - li * g.tile_w;
+                const int i = pi0 + li, j = pj0 + lj;
+                const int node = sub / gk;
+                if (r == 0) u0 = sub - node * gk;
+                const int a = node / Sk, b = node - a * Sk;
+                const bool active = pl < npix && i < g.res && j < g.res;
+                const float th = ((float)i + 0.5f + 0.5f * g.gl_x[cur_level - 1][a]) * g.cell;
+                const float ph = ((float)j + 0.5f + 0.5f * g.gl_x[cur_level - 1][b]) * g.cell;
+                float st, ct, sp, cp;
+                sincosf(th, &st, &ct);
+                sincosf(ph, &sp, &cp);
+                const float lx = st * cp, lz = st * sp;
+                nx[r] = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
+                ny[r] = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
+                nz[r] = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
+                nv[r] = lz;  // n . v exactly, the frame is orthonormal
+                const float mm = fminf(fmaxf(1.f - lz, 0.f), 1.f);
+                Fi[r] = (mm * mm) * (mm * mm) * mm;
+                wq[r] = active ? g.gl_w[cur_level - 1][a] * g.gl_w[cur_level - 1][b] : 0.f;
+                // F D G1(n.v) G1(n.d) / (4 n.v) = F x / (q^2 (x + sq)) / (pi alpha^2 (n.v + sqrt((n.v)^2 (1-a^2) + a^2)))
+                const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
+                mult[r] = lz > 0.f ? wq[r] / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+            }
+        }
         const int stage = it & 1;
         float* raw = raw0 + stage * RAW_FLOATS;
-        const int ty = cur / g.ttiles_x, tx = cur - ty * g.ttiles_x;
+        const int tile = tbeg + list[it];
+        const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
         if (g.use_tma) {
             mbar_wait(&bars[stage], (it >> 1) & 1);
         } else {
@@ -270,13 +361,12 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         }
         __syncthreads();  // records ready, raw[stage] free
 
-        const int nn = next_visible(nxt + 1);
-        if (g.use_tma && tid == 0 && nn < tend) {
+        if (g.use_tma && tid == 0 && it + 2 < nlist) {
             fence_proxy_async();
-            issue(nn, stage);
+            issue(it + 2, stage);
         }
 
-        // ---- gather: every thread x every record ---------------------------------------------------------------
+        // ---- gather: my 4 slots x my share of the tile's records ------------------------------------------------
         float acc[SUBS_PER_THREAD][6];
 #pragma unroll
         for (int r = 0; r < SUBS_PER_THREAD; ++r)
@@ -284,7 +374,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
             for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
 
 #pragma unroll 2
-        for (int t = 0; t < TILE_TEXELS; ++t) {
+        for (int t = u0; t < TILE_TEXELS; t += gk) {
             const float4 h = rec[t * 3 + 0];
             const float4 s = rec[t * 3 + 1];
             float4 d4;
@@ -299,7 +389,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 const float q = 1.f + sin2 * rc.inv_a2m1;             // cos^2 + sin^2 / alpha^2
                 const float xc = fmaxf(x, 0.f);                       // below the horizon: weight 0, denominator > 0
                 const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
-                const float ws = xc * fast_rcp(q * q * (xc + sq));    // D G1(n.d) up to per-sub-normal constants
+                const float ws = xc * fast_rcp(q * q * (xc + sq));    // D G1(n.d) up to per-slot constants
                 acc[r][0] += ws * s.y;
                 acc[r][1] += ws * s.z;
                 acc[r][2] += ws * s.w;
@@ -317,28 +407,30 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 }
             }
         }
+        // two-level summation (per tile, then total) keeps the fp32 error near 1e-6; the per-slot constants and the
+        // Gauss-Legendre weight of the current level are applied here, once per tile
 #pragma unroll
-        for (int r = 0; r < SUBS_PER_THREAD; ++r)
+        for (int r = 0; r < SUBS_PER_THREAD; ++r) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) tot[r][c] += acc[r][c];  // two-level summation keeps fp32 error ~1e-6
+            for (int c = 0; c < 3; ++c) tot[r][c] += mult[r] * acc[r][c];
+            if (HAS_DIFFUSE) {
+#pragma unroll
+                for (int c = 3; c < 6; ++c) tot[r][c] += wq[r] * acc[r][c];
+            }
+        }
         __syncthreads();  // records free
-        cur = nxt;
-        nxt = nn;
     }
 
-    // ---- epilogue: per-sub-normal constants, Gauss-Legendre weights, per-pixel reduction ----------------------------
+    // ---- epilogue: per-pixel reduction over the S^2 slots in fixed order -----------------------------------------------
     float* resbuf = reinterpret_cast<float*>(rec);  // [SLOTS][3]
 #pragma unroll
     for (int r = 0; r < SUBS_PER_THREAD; ++r) {
         const int q = r * GATHER_THREADS + tid;
-        // F D G1(n.v) G1(n.d) / (4 n.v) = F x / (q^2 (x + sq)) * 1 / (pi alpha^2 (n.v + sqrt((n.v)^2 (1-a^2) + a^2)))
-        const float g1 = nv[r] + sqrtf(nv[r] * nv[r] * rc.one_m_a2 + rc.alpha2);
-        const float cs = nv[r] > 0.f ? 1.f / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float v = cs * tot[r][c];
+            float v = tot[r][c];
             if (HAS_DIFFUSE) v += rc.cdiff[c] * tot[r][3 + c];
-            resbuf[q * 3 + c] = wq[r] * v;
+            resbuf[q * 3 + c] = v;
         }
     }
     __syncthreads();
@@ -395,6 +487,8 @@ static RenderPlan make_plan(int N, int He, int We, int res, int S) {
     const long ntiles = (long)p.ttiles_x * p.ttiles_y;
     const long smax = ntiles / 4 > 0 ? ntiles / 4 : 1;
     if (s > smax) s = smax;
+    const long smin = (ntiles + MAX_LIST - 1) / MAX_LIST;  // a CTA schedules at most MAX_LIST tiles
+    if (s < smin) s = smin;
     if (s < 1) s = 1;
     p.splits = (int)s;
     return p;
@@ -475,7 +569,25 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     g.cull = 1;
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
     g.cell = (float)(M_PI / res);
-    gauss_legendre(S, g.gl_x, g.gl_w);
+    // footprint levels: power-of-two lattices below S when S is one of 2,4,8,16 (S^2 then divides the 256 threads);
+    // any other S runs as a single level
+    g.nlev = 0;
+    const bool pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
+    const char* lv = getenv("DRM_RENDER_LEVELS");  // "0" disables the hierarchy (debugging / validation)
+    const bool hierarchy = pow2 && !(lv && lv[0] == '0');
+    if (hierarchy)
+        for (int sk = 1, ti = 0; sk < S; sk *= 2, ++ti) {
+            g.lev_S[g.nlev] = sk;
+            g.lev_tidx[g.nlev] = ti;
+            gauss_legendre(sk, g.gl_x[g.nlev], g.gl_w[g.nlev]);
+            ++g.nlev;
+        }
+    g.lev_S[g.nlev] = S;
+    g.lev_tidx[g.nlev] = MAX_LEVELS - 1;
+    gauss_legendre(S, g.gl_x[g.nlev], g.gl_w[g.nlev]);
+    ++g.nlev;
+    float level_scale = 0.3f;  // thresholds of render_setup_kernel are conservative; 0.3 measured (scripts/levels_probe.py)
+    if (const char* ls = getenv("DRM_RENDER_LEVEL_SCALE")) level_scale = (float)atof(ls);
 
     // TMA descriptor over env viewed as [B][He][3*We] fp32; box = 32 rows x 96 floats of one map
     CUtensorMap tmap;
@@ -502,9 +614,9 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
 
     const int tb = 128;
     render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(w.sin_t, w.cos_t, w.sin_p, w.cos_p, He, We);
-    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, w.rc);
+    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale, w.rc);
 
-    const size_t smem = 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float) + 64;
+    const size_t smem = 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float) + 16 + 64 + MAX_LIST * 3;
     DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.tiles_x * p.tiles_y, N, p.splits);

@@ -37,15 +37,14 @@ def _slots(names: Sequence[str]) -> List[int]:
 
 
 def auto_footprint(roughness: float, res: int = 128) -> int:
-    """Gauss-Legendre points per axis that resolve the cell average of a GGX lobe of this roughness."""
+    """Gauss-Legendre points per axis (1, 2, 4, 8 or 16) that resolve the cell average of a GGX lobe of this roughness
+    to ~2e-4: the ratio of cell width to lobe half-width decides (measured with the fp64 oracle)."""
     alpha = max(float(roughness) ** 2, 1e-3)
-    ratio = (torch.pi / res) / alpha  # cell width over lobe half-width in normal space
+    ratio = (torch.pi / res) / alpha
     if ratio < 0.1:
         return 1
     if ratio < 0.6:
         return 2
-    if ratio < 1.2:
-        return 3
     if ratio < 2.0:
         return 4
     if ratio < 4.0:

@@ -90,12 +90,13 @@ static void camera_frame(const double* view, double* vhat, double* left, double*
  * z6 = [metallic, base R, base G, base B, roughness, specular] (already clipped to [0,1]).
  * gl_x / gl_w: S Gauss-Legendre nodes on [-1,1] and weights normalised to sum 1.
  * terms: bit 0 = specular, bit 1 = diffuse.
+ * window: NULL, or {i0, i1, j0, j1}: only cells i0 <= i < i1, j0 <= j < j1 are evaluated (the rest of out stays 0).
  * out: [res, res, 3] doubles.
  */
 int drm_oracle_render_records(const double* rec_dir, const double* rec_E, long T,
                               const double* z6, const double* view3, int flip,
                               int res, int S, const double* gl_x, const double* gl_w,
-                              double alpha_min, int terms, double* out) {
+                              double alpha_min, int terms, const int* window, double* out) {
     const double m = z6[0], rough = z6[4], specular = z6[5];
     const double base[3] = {z6[1], z6[2], z6[3]};
     double alpha = rough * rough;
@@ -127,6 +128,10 @@ int drm_oracle_render_records(const double* rec_dir, const double* rec_E, long T
     for (int pix = 0; pix < res * res; ++pix) {
         int i = pix / res, j = pix % res;
         double acc[3] = {0, 0, 0};
+        if (window && (i < window[0] || i >= window[1] || j < window[2] || j >= window[3])) {
+            out[3 * pix + 0] = out[3 * pix + 1] = out[3 * pix + 2] = 0.0;
+            continue;
+        }
         for (int a = 0; a < S; ++a)
             for (int b = 0; b < S; ++b) {
                 double th = (i + 0.5 + 0.5 * gl_x[a]) * cell;

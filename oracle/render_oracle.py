@@ -40,7 +40,8 @@ def _load():
         _lib = ctypes.CDLL(str(_SO))
         dp = ctypes.POINTER(ctypes.c_double)
         _lib.drm_oracle_render_records.argtypes = [dp, dp, ctypes.c_long, dp, dp, ctypes.c_int, ctypes.c_int,
-                                                   ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, dp]
+                                                   ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_int), dp]
         _lib.drm_oracle_render_records.restype = ctypes.c_int
         _lib.drm_oracle_num_threads.restype = ctypes.c_int
     return _lib
@@ -87,7 +88,7 @@ def default_alpha_min(He: int) -> float:
     return max(1e-3, 1.25 * np.pi / He)
 
 
-def render_records(dirs, E, z6, view, res, S=1, flip=False, alpha_min=1e-3, terms=3) -> np.ndarray:
+def render_records(dirs, E, z6, view, res, S=1, flip=False, alpha_min=1e-3, terms=3, window=None) -> np.ndarray:
     lib = _load()
     dirs = np.ascontiguousarray(dirs, dtype=np.float64)
     E = np.ascontiguousarray(E, dtype=np.float64)
@@ -96,18 +97,20 @@ def render_records(dirs, E, z6, view, res, S=1, flip=False, alpha_min=1e-3, term
     gx, gw = gauss_legendre(S)
     out = np.zeros((res, res, 3), np.float64)
     dp = ctypes.POINTER(ctypes.c_double)
+    win = (ctypes.c_int * 4)(*[int(w) for w in window]) if window is not None else None
     rc = lib.drm_oracle_render_records(dirs.ctypes.data_as(dp), E.ctypes.data_as(dp), dirs.shape[0],
                                        z6.ctypes.data_as(dp), view.ctypes.data_as(dp), int(bool(flip)), int(res),
                                        int(S), gx.ctypes.data_as(dp), gw.ctypes.data_as(dp), float(alpha_min),
-                                       int(terms), out.ctypes.data_as(dp))
+                                       int(terms), win, out.ctypes.data_as(dp))
     if rc != 0:
         raise MemoryError("render oracle allocation failed")
     return out
 
 
-def render_oracle(env, z, view, res, *, names=None, S=1, flip=False, alpha_min=None, terms=3) -> np.ndarray:
+def render_oracle(env, z, view, res, *, names=None, S=1, flip=False, alpha_min=None, terms=3, window=None) -> np.ndarray:
     """Canonical render of one refmap: [res,res,3] fp64.  ``z`` is either the 6-vector in the shipped order
-    [metallic,R,G,B,roughness,specular] (configs/drmnet/train_drmnet.yaml:26) or named by ``names``."""
+    [metallic,R,G,B,roughness,specular] (configs/drmnet/train_drmnet.yaml:26) or named by ``names``.  ``window`` =
+    (i0, i1, j0, j1) restricts the evaluation to a block of cells (the rest of the output is 0)."""
     env = np.asarray(env)
     if names is None:
         names = list(_NAME_TO_SLOT)
@@ -115,7 +118,7 @@ def render_oracle(env, z, view, res, *, names=None, S=1, flip=False, alpha_min=N
     if alpha_min is None:
         alpha_min = default_alpha_min(env.shape[0])
     dirs, E = env_records(env)
-    return render_records(dirs, E, z6, view, res, S=S, flip=flip, alpha_min=alpha_min, terms=terms)
+    return render_records(dirs, E, z6, view, res, S=S, flip=flip, alpha_min=alpha_min, terms=terms, window=window)
 
 
 def rel_l2(a, b) -> float:

@@ -149,3 +149,48 @@ def test_dropin_class_statefulness_and_attributes():
     bad = env.clone(); bad[0, 0, 0] = float("nan")
     with pytest.raises(AssertionError):
         r.rendering(z, BRDF_PARAM_NAMES, envmap=bad)
+
+
+# ---- footprint hierarchy (coarser lattices for texel tiles far from the lobe) --------------------------------------
+def _with_levels(flag, fn):
+    import os
+    old = os.environ.get("DRM_RENDER_LEVELS")
+    os.environ["DRM_RENDER_LEVELS"] = flag
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("DRM_RENDER_LEVELS", None)
+        else:
+            os.environ["DRM_RENDER_LEVELS"] = old
+
+
+@pytest.mark.parametrize("case", [("z0_mirror", 16), ("near_mirror_schedule", 16), ("glossy_metal", 4), ("mixed", 2)])
+def test_hierarchy_matches_single_level_full_size(case):
+    """BASELINE size (2000x1000 -> 128x128): the level schedule against the single-level evaluation of the same
+    canonical sum (every sub-normal x every texel), all 16 384 pixels."""
+    zname, S = case
+    env = synthetic_envmap(1000, 2000, seed=1004, device=DEV)[None]
+    z = torch.tensor([Z_CASES[zname]])
+    v = torch.tensor([VIEWS[2]])
+    hier = _with_levels("1", lambda: render_batch(env, z, v, res=128, footprint_S=S))
+    flat = _with_levels("0", lambda: render_batch(env, z, v, res=128, footprint_S=S))
+    torch.cuda.synchronize()
+    assert rel_l2(hier.cpu().numpy(), flat.cpu().numpy()) <= 7e-5
+
+
+@pytest.mark.parametrize("zname", ["z0_mirror", "glossy_metal"])
+def test_hierarchy_parity_vs_oracle_windows(zname):
+    """S = 16 at res 128 on a 1000x500 map against the fp64 oracle, on two 4x4-cell windows: the brightest cell of the
+    refmap (a light source in the lobe) and a dim one (tail contributions only)."""
+    env = synthetic_envmap(500, 1000, seed=1004)
+    z = Z_CASES[zname]
+    ours = _render(env[None], [z], [VIEWS[0]], 128, 16, channel_first=False)[0]
+    lum = ours.sum(-1)
+    bi, bj = np.unravel_index(np.argmax(lum[8:-8, 8:-8]), lum[8:-8, 8:-8].shape)
+    bi, bj = int(bi) + 8, int(bj) + 8
+    for (i0, j0) in ((bi - 2, bj - 2), (60, 20)):
+        win = (i0, i0 + 4, j0, j0 + 4)
+        ref = render_oracle(env, z, VIEWS[0], 128, S=16, window=win)
+        a, b = ours[win[0]:win[1], win[2]:win[3]], ref[win[0]:win[1], win[2]:win[3]]
+        assert rel_l2(a, b) <= TOL, (zname, win, rel_l2(a, b))
