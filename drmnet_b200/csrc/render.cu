@@ -7,12 +7,20 @@
 //   out[k, i, j, c] = sum_{a,b < S} w_a w_b  sum_texels  f_c(d_t; v_k, n(theta_i,a, phi_j,b); z_k) E[t, c] dOmega_t
 //
 // with S x S Gauss-Legendre sub-normals per refmap cell (the box pixel filter) and the texel-centre quadrature of the
-// emitter.  One CTA owns a tile of sub-normals of one render and streams 32x32-texel envmap tiles through shared
+// emitter.  One CTA owns a tile of refmap cells of one render and streams 32x32-texel envmap tiles through shared
 // memory with TMA (cp.async.bulk.tensor, double buffered, mbarrier completion); a cooperative transform turns each raw
 // tile into per-texel records (half vector, Fresnel-weighted radiance * solid angle, retro-reflection factor) that are
-// pixel independent, then every thread gathers all 1024 records for its 4 sub-normals from shared memory (broadcast
-// LDS.128).  The kernel is bound by the FP32/MUFU pipes (about 34 instructions per (sub-normal, texel) pair), not by
-// HBM: each envmap byte is reused by every sub-normal of the render out of L2.
+// pixel independent, then every thread gathers records for its 4 sub-normal slots from shared memory (LDS.128).
+//
+// Three controlled reductions of the pair count keep the result within ~5e-5 of the full sum (tests):
+//   * footprint levels: a texel tile far (in half-vector space) from the CTA's normals is integrated over the cell
+//     with a coarser Gauss-Legendre lattice (16x16 -> 8x8 -> 4x4 -> 2x2 -> 1x1); the slots freed by the coarser
+//     lattice split the tile's texels among themselves, so no thread idles;
+//   * the diffuse lobe, which varies on the scale of a radian, is gathered from a 4x4-texel energy-centroid coarsening
+//     of the envmap (built per call by env_coarsen_kernel) when those cells are small enough;
+//   * a very rough specular lobe (alpha >= 4x4-cell size / 0.026) is gathered from the same coarsening.
+// The kernel is bound by the FP32/MUFU pipes (about 22 instructions per (slot, texel) pair for the specular lobe, 14
+// for the diffuse one), not by HBM: each envmap byte is reused by every slot of the render out of L2.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,35 +32,39 @@ namespace drm {
 static constexpr int GATHER_THREADS = 256;
 static constexpr int SUBS_PER_THREAD = 4;
 static constexpr int SLOTS = GATHER_THREADS * SUBS_PER_THREAD;  // sub-normal slots per CTA
-static constexpr int TT = 32;                                   // texel tile edge
+static constexpr int TT = 32;                                   // tile edge in texels (or coarse cells)
 static constexpr int TILE_TEXELS = TT * TT;
-static constexpr int RAW_FLOATS = TT * TT * 3;
 static constexpr int REC_FLOATS = 12;
-static constexpr int MAX_LEVELS = 5;      // footprint lattices 1,2,4,8,16 per axis
-static constexpr int MAX_LIST = 2048;     // texel tiles one CTA can schedule (plan splits larger maps)
+static constexpr int MAX_LEVELS = 5;   // footprint lattices 1,2,4,8,16 per axis
+static constexpr int MAX_LIST = 2048;  // tiles one CTA can schedule (the plan splits larger maps)
+static constexpr int COARSE = 4;       // coarsening factor of the energy-centroid map
+static constexpr int COARSE_FLOATS = 6;  // centroid direction + radiance * solid angle per coarse cell
+
+// which launch serves which part of a render
+enum : int { ROUTE_SPEC_RAW = 1, ROUTE_BOTH_RAW = 2, ROUTE_DIFF_COARSE = 4, ROUTE_BOTH_COARSE = 8 };
 
 struct RenderConst {  // per render
     float vhat[3], left[3], upp[3];  // camera frame of look_at(v, 0, +Y); `left` carries the flip sign
     float m, rough, alpha2, inv_a2m1, one_m_a2, eta;
     float base[3], cdiff[3];
     float thr[MAX_LEVELS];  // half-vector-space distance beyond which footprint level k is accurate enough
-    int env, has_diffuse;
+    int env, route;
 };
 
 struct GatherArgs {
-    const float* env;
+    const float* src;  // raw envmaps [B,He,We,3] or coarse maps [B,Hm,Wm,6]
     const RenderConst* rc;
     const float *sin_t, *cos_t, *sin_p, *cos_p;
-    float* out;
-    float* partial;
+    float* slab;  // [splits][N][res*res][3] partial sums of this launch
     int B, He, We, N, res, S;
+    int Hm, Wm;   // rows / columns of the map this launch reads (He,We or the coarse dims)
     int tile_w, tile_h, tiles_x, tiles_y;
     int ttiles_x, ttiles_y, splits;
-    int channel_first, use_tma, cull;
-    int nlev;                 // number of footprint levels used by this launch
-    int lev_S[MAX_LEVELS];    // lattice size per axis of level k (ascending; the last one is S)
-    int lev_tidx[MAX_LEVELS]; // log2(lev_S[k]): index into RenderConst::thr
-    float domega_k, cell;
+    int use_tma, cull, route_mask;
+    int nlev;                  // number of footprint levels used by this launch
+    int lev_S[MAX_LEVELS];     // lattice size per axis of level k (ascending; the last one is S)
+    int lev_tidx[MAX_LEVELS];  // log2(lev_S[k]): index into RenderConst::thr
+    float domega_k, cell, dth_cell, dph_cell;  // dth/dph: angular size of one map cell
     float gl_x[MAX_LEVELS][16], gl_w[MAX_LEVELS][16];
 };
 
@@ -70,11 +82,48 @@ __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, f
     }
 }
 
-// clip z to [0,1] (mitsuba3_utils.py:239,242), derive the BSDF constants and the camera frame (:235-236)
+// K3: 4x4-texel energy-centroid coarsening.  Cell = {unit centroid direction (luminance * solid-angle weighted),
+// sum of radiance * solid angle per channel}: placing the cell's energy at its centroid cancels the first-order error
+// of evaluating a smooth lobe once per cell.
+__global__ void env_coarsen_kernel(const float* __restrict__ env, const float* __restrict__ sin_t,
+                                   const float* __restrict__ cos_t, const float* __restrict__ sin_p,
+                                   const float* __restrict__ cos_p, int B, int He, int We, int Hc, int Wc,
+                                   float domega_k, float* __restrict__ coarse) {
+    const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (cell >= (long)B * Hc * Wc) return;
+    const int C = (int)(cell % Wc), R = (int)((cell / Wc) % Hc), b = (int)(cell / ((long)Wc * Hc));
+    const float* src = env + (size_t)b * He * We * 3;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int dr = 0; dr < COARSE; ++dr) {
+        const int r = R * COARSE + dr;
+        if (r >= He) break;
+        const float st = sin_t[r], ct = cos_t[r], dom = domega_k * st;
+        for (int dc = 0; dc < COARSE; ++dc) {
+            const int c = C * COARSE + dc;
+            if (c >= We) break;
+            const float* e = src + ((size_t)r * We + c) * 3;
+            const float er = e[0] * dom, eg = e[1] * dom, eb = e[2] * dom;
+            const float dx = st * sin_p[c], dy = ct, dz = -st * cos_p[c];
+            const float w = er + eg + eb;
+            m0 += er; m1 += eg; m2 += eb;
+            cx += w * dx; cy += w * dy; cz += w * dz;
+            gx += dom * dx; gy += dom * dy; gz += dom * dz;  // geometric centre, used when the cell is black
+        }
+    }
+    float n2 = cx * cx + cy * cy + cz * cz;
+    if (!(n2 > 1e-30f)) { cx = gx; cy = gy; cz = gz; n2 = cx * cx + cy * cy + cz * cz; }
+    const float inv = rsqrtf(fmaxf(n2, 1e-38f));
+    float* o = coarse + (size_t)cell * COARSE_FLOATS;
+    o[0] = cx * inv; o[1] = cy * inv; o[2] = cz * inv;
+    o[3] = m0; o[4] = m1; o[5] = m2;
+}
+
+// clip z to [0,1] (mitsuba3_utils.py:239,242), derive the BSDF constants, the camera frame (:235-236), the footprint
+// level thresholds and the routing of the render's terms to the launches
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N,
-                                    int B, float alpha_min, float cell, float level_scale,
-                                    RenderConst* __restrict__ rc) {
+                                    int B, float alpha_min, float cell, float level_scale, float coarse_h,
+                                    int coarse_diffuse_ok, RenderConst* __restrict__ rc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     RenderConst c;
@@ -93,15 +142,21 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
     // Gauss-Legendre error ~ K_S (cell/d)^(2S) weighted by the tail mass (alpha/d)^2 is held near 1e-5.
     {
         const float ca = cell * alpha;
-        c.thr[0] = 21.0f * sqrtf(ca);                                  // 1 x 1
+        c.thr[0] = 21.0f * sqrtf(ca);                                      // 1 x 1
         c.thr[1] = 7.5f * powf(cell, 2.f / 3.f) * powf(alpha, 1.f / 3.f);  // 2 x 2
-        c.thr[2] = 2.4f * powf(cell, 0.8f) * powf(alpha, 0.2f);        // 4 x 4
+        c.thr[2] = 2.4f * powf(cell, 0.8f) * powf(alpha, 0.2f);            // 4 x 4
         c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);  // 8 x 8
-        c.thr[4] = 0.f;                                                // 16 x 16
+        c.thr[4] = 0.f;                                                    // 16 x 16
         for (int i = 0; i < MAX_LEVELS - 1; ++i) c.thr[i] = level_scale * fmaxf(c.thr[i], 6.f * alpha);
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
-    c.has_diffuse = (c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f) ? 1 : 0;
+    const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
+    // routing: measured error of one evaluation per 4x4 cell ~ 0.03 (h/alpha)^2 for the GGX lobe and ~ 0.18 h^2 for the
+    // diffuse lobe (h = cell size in radians, oracle study in DESIGN.md); each is held near 2-3e-5
+    const bool spec_coarse = coarse_h > 0.f && coarse_h <= 0.026f * alpha;
+    if (spec_coarse) c.route = ROUTE_BOTH_COARSE;
+    else if (!has_diffuse) c.route = ROUTE_SPEC_RAW;
+    else c.route = coarse_diffuse_ok ? (ROUTE_SPEC_RAW | ROUTE_DIFF_COARSE) : ROUTE_BOTH_RAW;
     float vx = view3[3 * k], vy = view3[3 * k + 1], vz = view3[3 * k + 2];
     float inv = rsqrtf(vx * vx + vy * vy + vz * vz);
     vx *= inv; vy *= inv; vz *= inv;
@@ -130,17 +185,17 @@ __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
     return 0.5f * (a_s * a_s + a_p * a_p);
 }
 
-// Classify one texel tile for a CTA whose normals lie in the cone (axis a, radius beta):
-//   0      no normal of the cone sees any texel of the tile (n.d <= 0 everywhere): skipped
+// Classify one map tile for a CTA whose normals lie in the cone (axis a, radius beta):
+//   0      no normal of the cone sees any direction of the tile (n.d <= 0 everywhere): skipped
 //   1+k    footprint level k (0 = 1x1 lattice ... nlev-1 = full S x S lattice) chosen from the distance, in
 //          half-vector space, between the cone of normals and the tile's half vectors h = normalize(v + d)
 __device__ __forceinline__ int classify_tile(const GatherArgs& g, const float* __restrict__ vhat,
                                              const float* __restrict__ thr, int tile, float ax, float ay, float az,
                                              float beta) {
     const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
-    const int r0 = ty * TT, r1 = min(r0 + TT, g.He), c0 = tx * TT, c1 = min(c0 + TT, g.We);
-    const float dth = 0.5f * (r1 - r0) * (3.14159265f / g.He), dph = 0.5f * (c1 - c0) * (6.2831853f / g.We);
-    const float thc = 0.5f * (r0 + r1) * (3.14159265f / g.He), phc = 0.5f * (c0 + c1) * (6.2831853f / g.We);
+    const int r0 = ty * TT, r1 = min(r0 + TT, g.Hm), c0 = tx * TT, c1 = min(c0 + TT, g.Wm);
+    const float dth = 0.5f * (r1 - r0) * g.dth_cell, dph = 0.5f * (c1 - c0) * g.dph_cell;
+    const float thc = fminf(0.5f * (r0 + r1) * g.dth_cell, 3.14159265f), phc = 0.5f * (c0 + c1) * g.dph_cell;
     float st, ct, sp, cp;
     sincosf(thc, &st, &ct);
     sincosf(phc, &sp, &cp);
@@ -163,22 +218,26 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const float* _
     return g.nlev;
 }
 
-template <bool HAS_DIFFUSE>
+// TERMS: 1 = specular lobe, 2 = diffuse lobe, 3 = both.  COARSE_SRC: the map is the 4x4 energy-centroid coarsening.
+template <int TERMS, bool COARSE_SRC>
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
 render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs g) {
+    constexpr int RAW_FLOATS = TILE_TEXELS * (COARSE_SRC ? COARSE_FLOATS : 3);
+    constexpr int ROW_FLOATS = TT * (COARSE_SRC ? COARSE_FLOATS : 3);
+    constexpr bool SPEC = (TERMS & 1) != 0, DIFF = (TERMS & 2) != 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* raw0 = reinterpret_cast<float*>(smem_raw);
     float4* rec = reinterpret_cast<float4*>(smem_raw + 2 * RAW_FLOATS * sizeof(float));
     unsigned char* tail = smem_raw + 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                 // 2 mbarriers
-    int* scan_ws = reinterpret_cast<int*>(tail + 16);                     // 8 warp sums + level starts
-    uint16_t* list = reinterpret_cast<uint16_t*>(tail + 16 + 64);         // [MAX_LIST] tiles ordered by level
-    uint8_t* lvl = reinterpret_cast<uint8_t*>(tail + 16 + 64 + MAX_LIST * 2);  // [MAX_LIST]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                        // 2 mbarriers
+    int* scan_ws = reinterpret_cast<int*>(tail + 16);                            // 8 warp sums + level ends
+    uint16_t* list = reinterpret_cast<uint16_t*>(tail + 16 + 64);                // [MAX_LIST] tiles ordered by level
+    uint8_t* lvl = reinterpret_cast<uint8_t*>(tail + 16 + 64 + MAX_LIST * 2);    // [MAX_LIST]
 
     const int tid = threadIdx.x;
     const int k = blockIdx.y;
     const RenderConst rc = g.rc[k];
-    if (HAS_DIFFUSE != (rc.has_diffuse != 0)) return;  // the other instantiation serves this render
+    if (!(rc.route & g.route_mask)) return;  // another launch serves this render (uniform per CTA)
 
     const int ptile = blockIdx.x;
     const int pty = ptile / g.tiles_x, ptx = ptile - pty * g.tiles_x;
@@ -209,13 +268,14 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         if (g.use_tma) tma_prefetch_desc(&tmap);
     }
 
-    // ---- schedule: classify my texel tiles, then order them by footprint level (coarse first, tile order inside) ----
+    // ---- schedule: classify my tiles, then order them by footprint level (coarse first, tile order inside) ----------
+    // texel splits interleave the tiles (tile = z + e * splits) so that the few tiles near the lobe, which run on
+    // the fine lattices, spread over all splits
     const int ntiles = g.ttiles_x * g.ttiles_y;
-    const int per = (ntiles + g.splits - 1) / g.splits;
-    const int tbeg = blockIdx.z * per, tend = min(tbeg + per, ntiles);
-    const int nmine = tend - tbeg;
+    const int tbeg = blockIdx.z, tstep = g.splits;
+    const int nmine = (ntiles - tbeg + tstep - 1) / tstep;
     for (int e = tid; e < nmine; e += GATHER_THREADS)
-        lvl[e] = (uint8_t)classify_tile(g, g.rc[k].vhat, g.rc[k].thr, tbeg + e, ax, ay, az, beta);
+        lvl[e] = (uint8_t)classify_tile(g, g.rc[k].vhat, g.rc[k].thr, tbeg + e * tstep, ax, ay, az, beta);
     __syncthreads();
     int nlist = 0;
     {
@@ -260,10 +320,10 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         for (int c = 0; c < 6; ++c) tot[r][c] = 0.f;
 
     auto issue = [&](int e, int stage) {
-        const int tile = tbeg + list[e];
+        const int tile = tbeg + list[e] * tstep;
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
         mbar_arrive_expect_tx(&bars[stage], RAW_FLOATS * sizeof(float));
-        tma_load_3d(raw0 + stage * RAW_FLOATS, &tmap, &bars[stage], tx * TT * 3, ty * TT, rc.env);
+        tma_load_3d(raw0 + stage * RAW_FLOATS, &tmap, &bars[stage], tx * ROW_FLOATS, ty * TT, rc.env);
     };
     if (g.use_tma && tid == 0) {
         if (0 < nlist) issue(0, 0);
@@ -281,8 +341,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
 
     for (int it = 0; it < nlist; ++it) {
         if (it >= level_end) {
-            // next non-empty level
-            do { ++cur_level; level_end = scan_ws[8 + cur_level]; } while (it >= level_end);
+            do { ++cur_level; level_end = scan_ws[8 + cur_level]; } while (it >= level_end);  // next non-empty level
             const int Sk = g.lev_S[cur_level - 1];
             const int ratio = g.S / Sk;
             gk = hier ? ratio * ratio : 1;
@@ -316,48 +375,59 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         }
         const int stage = it & 1;
         float* raw = raw0 + stage * RAW_FLOATS;
-        const int tile = tbeg + list[it];
+        const int tile = tbeg + list[it] * tstep;
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
         if (g.use_tma) {
             mbar_wait(&bars[stage], (it >> 1) & 1);
         } else {
-            // plain-load fallback for maps whose row pitch is not a multiple of 16 bytes
-            const float* src = g.env + (size_t)rc.env * g.He * g.We * 3;
+            // plain-load staging for maps whose row pitch is not a multiple of 16 bytes
+            const int row_floats = g.Wm * (COARSE_SRC ? COARSE_FLOATS : 3);
+            const float* src = g.src + (size_t)rc.env * g.Hm * row_floats;
             for (int e = tid; e < RAW_FLOATS; e += GATHER_THREADS) {
-                const int lr = e / (TT * 3), lc3 = e - lr * (TT * 3);
-                const int r = ty * TT + lr, c3 = tx * TT * 3 + lc3;
-                raw[e] = (r < g.He && c3 < g.We * 3) ? src[(size_t)r * g.We * 3 + c3] : 0.f;
+                const int lr = e / ROW_FLOATS, lc = e - lr * ROW_FLOATS;
+                const int r = ty * TT + lr, c = tx * ROW_FLOATS + lc;
+                raw[e] = (r < g.Hm && c < row_floats) ? src[(size_t)r * row_floats + c] : 0.f;
             }
             __syncthreads();
         }
 
-        // ---- transform: raw RGB -> pixel-independent per-texel records ------------------------------------------
+        // ---- transform: raw tile -> pixel-independent records {h, |v+d|, Rr, E dOmega F_c, E dOmega} -----------------
 #pragma unroll
         for (int u = 0; u < TILE_TEXELS / GATHER_THREADS; ++u) {
             const int t = u * GATHER_THREADS + tid;
             const int lr = t / TT, lc = t - lr * TT;
-            const int r = min(ty * TT + lr, g.He - 1), c = min(tx * TT + lc, g.We - 1);
-            const float st = g.sin_t[r], ct = g.cos_t[r], sp = g.sin_p[c], cp = g.cos_p[c];
-            const float dx = st * sp, dy = ct, dz = -st * cp;
-            const float dom = g.domega_k * st;
+            float dx, dy, dz, er, eg, eb;
+            if (COARSE_SRC) {
+                const float* cellp = raw + lr * ROW_FLOATS + lc * COARSE_FLOATS;
+                dx = cellp[0]; dy = cellp[1]; dz = cellp[2];
+                er = cellp[3]; eg = cellp[4]; eb = cellp[5];
+            } else {
+                const int r = min(ty * TT + lr, g.He - 1), c = min(tx * TT + lc, g.We - 1);
+                const float st = g.sin_t[r], ct = g.cos_t[r], sp = g.sin_p[c], cp = g.cos_p[c];
+                dx = st * sp; dy = ct; dz = -st * cp;
+                const float dom = g.domega_k * st;
+                er = raw[lr * ROW_FLOATS + lc * 3 + 0] * dom;
+                eg = raw[lr * ROW_FLOATS + lc * 3 + 1] * dom;
+                eb = raw[lr * ROW_FLOATS + lc * 3 + 2] * dom;
+            }
             const float vd = rc.vhat[0] * dx + rc.vhat[1] * dy + rc.vhat[2] * dz;
             const float len2 = fmaxf(2.f + 2.f * vd, 1e-12f);
             const float inv_len = rsqrtf(len2);
             const float len = len2 * inv_len;
             const float vh = 0.5f * len;
-            const float Fd = fresnel_dielectric(vh, rc.eta);
-            const float mm = fminf(fmaxf(1.f - vh, 0.f), 1.f);
-            const float sw = (mm * mm) * (mm * mm) * mm;
-            const float er = raw[lr * TT * 3 + lc * 3 + 0] * dom;
-            const float eg = raw[lr * TT * 3 + lc * 3 + 1] * dom;
-            const float eb = raw[lr * TT * 3 + lc * 3 + 2] * dom;
-            const float fr = (1.f - rc.m) * Fd + rc.m * (rc.base[0] + (1.f - rc.base[0]) * sw);
-            const float fg = (1.f - rc.m) * Fd + rc.m * (rc.base[1] + (1.f - rc.base[1]) * sw);
-            const float fb = (1.f - rc.m) * Fd + rc.m * (rc.base[2] + (1.f - rc.base[2]) * sw);
             rec[t * 3 + 0] = make_float4((rc.vhat[0] + dx) * inv_len, (rc.vhat[1] + dy) * inv_len,
                                          (rc.vhat[2] + dz) * inv_len, len);
+            float fr = 0.f, fg = 0.f, fb = 0.f;
+            if (SPEC) {
+                const float Fd = fresnel_dielectric(vh, rc.eta);
+                const float mm = fminf(fmaxf(1.f - vh, 0.f), 1.f);
+                const float sw = (mm * mm) * (mm * mm) * mm;
+                fr = (1.f - rc.m) * Fd + rc.m * (rc.base[0] + (1.f - rc.base[0]) * sw);
+                fg = (1.f - rc.m) * Fd + rc.m * (rc.base[1] + (1.f - rc.base[1]) * sw);
+                fb = (1.f - rc.m) * Fd + rc.m * (rc.base[2] + (1.f - rc.base[2]) * sw);
+            }
             rec[t * 3 + 1] = make_float4(2.f * rc.rough * vh * vh, er * fr, eg * fg, eb * fb);
-            rec[t * 3 + 2] = make_float4(er, eg, eb, 0.f);
+            if (DIFF) rec[t * 3 + 2] = make_float4(er, eg, eb, 0.f);
         }
         __syncthreads();  // records ready, raw[stage] free
 
@@ -378,22 +448,24 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
             const float4 h = rec[t * 3 + 0];
             const float4 s = rec[t * 3 + 1];
             float4 d4;
-            if (HAS_DIFFUSE) d4 = rec[t * 3 + 2];
+            if (DIFF) d4 = rec[t * 3 + 2];
 #pragma unroll
             for (int r = 0; r < SUBS_PER_THREAD; ++r) {
                 const float ex = nx[r] - h.x, ey = ny[r] - h.y, ez = nz[r] - h.z;
                 const float u2 = ex * ex + ey * ey + ez * ez;         // 2 (1 - n.h), no cancellation
                 const float nh = 1.f - 0.5f * u2;
                 const float x = h.w * nh - nv[r];                     // n.d = |v+d| n.h - n.v
-                const float sin2 = u2 * (1.f - 0.25f * u2);           // 1 - (n.h)^2
-                const float q = 1.f + sin2 * rc.inv_a2m1;             // cos^2 + sin^2 / alpha^2
                 const float xc = fmaxf(x, 0.f);                       // below the horizon: weight 0, denominator > 0
-                const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
-                const float ws = xc * fast_rcp(q * q * (xc + sq));    // D G1(n.d) up to per-slot constants
-                acc[r][0] += ws * s.y;
-                acc[r][1] += ws * s.z;
-                acc[r][2] += ws * s.w;
-                if (HAS_DIFFUSE) {
+                if (SPEC) {
+                    const float sin2 = u2 * (1.f - 0.25f * u2);       // 1 - (n.h)^2
+                    const float q = 1.f + sin2 * rc.inv_a2m1;         // cos^2 + sin^2 / alpha^2
+                    const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
+                    const float ws = xc * fast_rcp(q * q * (xc + sq));  // D G1(n.d) up to per-slot constants
+                    acc[r][0] += ws * s.y;
+                    acc[r][1] += ws * s.z;
+                    acc[r][2] += ws * s.w;
+                }
+                if (DIFF) {
                     const float mm = 1.f - xc;
                     const float m2 = mm * mm;
                     const float Fo = m2 * m2 * mm;
@@ -411,9 +483,11 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         // Gauss-Legendre weight of the current level are applied here, once per tile
 #pragma unroll
         for (int r = 0; r < SUBS_PER_THREAD; ++r) {
+            if (SPEC) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) tot[r][c] += mult[r] * acc[r][c];
-            if (HAS_DIFFUSE) {
+                for (int c = 0; c < 3; ++c) tot[r][c] += mult[r] * acc[r][c];
+            }
+            if (DIFF) {
 #pragma unroll
                 for (int c = 3; c < 6; ++c) tot[r][c] += wq[r] * acc[r][c];
             }
@@ -428,8 +502,8 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         const int q = r * GATHER_THREADS + tid;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float v = tot[r][c];
-            if (HAS_DIFFUSE) v += rc.cdiff[c] * tot[r][3 + c];
+            float v = SPEC ? tot[r][c] : 0.f;
+            if (DIFF) v += rc.cdiff[c] * tot[r][3 + c];
             resbuf[q * 3 + c] = v;
         }
     }
@@ -442,36 +516,43 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         float v = 0.f;
         for (int s2 = 0; s2 < S2; ++s2) v += resbuf[(pl * S2 + s2) * 3 + c];
         const size_t pix = (size_t)i * g.res + j;
-        if (g.splits == 1) {
-            const size_t idx = g.channel_first ? ((size_t)k * 3 + c) * g.res * g.res + pix
-                                               : ((size_t)k * g.res * g.res + pix) * 3 + c;
-            g.out[idx] = v;
-        } else {
-            g.partial[(((size_t)blockIdx.z * g.N + k) * g.res * g.res + pix) * 3 + c] = v;
-        }
+        g.slab[(((size_t)blockIdx.z * g.N + k) * g.res * g.res + pix) * 3 + c] = v;
     }
 }
 
-__global__ void render_reduce_splits_kernel(const float* __restrict__ partial, float* __restrict__ out, int N, int res,
-                                            int splits, int channel_first) {
+struct SlabDesc {
+    const float* base;
+    int splits, route_mask;
+};
+
+// out = sum over the launches that served the render and over their texel splits, in fixed order (deterministic)
+__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3,
+                                      const RenderConst* __restrict__ rc, float* __restrict__ out, int N, int res,
+                                      int channel_first) {
     const size_t total = (size_t)N * res * res * 3;
     size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (o >= total) return;
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += partial[(size_t)s * total + o];  // fixed order: deterministic
     const int c = (int)(o % 3);
     const size_t pix = (o / 3) % ((size_t)res * res);
     const size_t k = o / 3 / ((size_t)res * res);
+    const int route = rc[k].route;
+    float v = 0.f;
+    const SlabDesc slabs[4] = {s0, s1, s2, s3};
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        if (slabs[l].base && (route & slabs[l].route_mask))
+            for (int s = 0; s < slabs[l].splits; ++s) v += slabs[l].base[(size_t)s * total + o];
     const size_t idx = channel_first ? (k * 3 + c) * res * res + pix : o;
     out[idx] = v;
 }
 
 struct RenderPlan {
-    int tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
+    int S, tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
 };
 
-static RenderPlan make_plan(int N, int He, int We, int res, int S) {
+static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S) {
     RenderPlan p;
+    p.S = S;
     int px = SLOTS / (S * S);
     int e = (int)floor(sqrt((double)px));
     if (e < 1) e = 1;
@@ -479,8 +560,8 @@ static RenderPlan make_plan(int N, int He, int We, int res, int S) {
     p.tile_w = p.tile_h = e;
     p.tiles_x = (res + e - 1) / e;
     p.tiles_y = (res + e - 1) / e;
-    p.ttiles_x = (We + TT - 1) / TT;
-    p.ttiles_y = (He + TT - 1) / TT;
+    p.ttiles_x = (Wm + TT - 1) / TT;
+    p.ttiles_y = (Hm + TT - 1) / TT;
     const long ctas = (long)p.tiles_x * p.tiles_y * N;
     const long want = 148L * 2 * 2;  // two waves of two resident CTAs per SM
     long s = (want + ctas - 1) / ctas;
@@ -494,19 +575,36 @@ static RenderPlan make_plan(int N, int He, int We, int res, int S) {
     return p;
 }
 
-struct RenderWs {
+struct RenderLayout {
+    int Hc, Wc;
+    bool coarse_enabled, coarse_diffuse_ok;
+    float coarse_h;
+    RenderPlan raw, diff, coarse;  // launches: spec/both on the raw map, diffuse on the coarse map, both on the coarse map
     RenderConst* rc;
-    float *sin_t, *cos_t, *sin_p, *cos_p, *partial;
+    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *slab_raw, *slab_diff, *slab_coarse;
 };
 
-static size_t render_carve(RenderWs& w, void* ws, int N, int He, int We, int res, const RenderPlan& p) {
+static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
+    L.Hc = (He + COARSE - 1) / COARSE;
+    L.Wc = (We + COARSE - 1) / COARSE;
+    L.coarse_h = (float)(COARSE * M_PI / He);
+    const char* cv = getenv("DRM_RENDER_COARSE");  // "0" disables the coarse-map routes (debugging / validation)
+    L.coarse_enabled = !(cv && cv[0] == '0') && He >= 8 * COARSE && We >= 8 * COARSE;
+    L.coarse_diffuse_ok = L.coarse_enabled && L.coarse_h <= 0.0135f;
+    L.raw = make_plan(N, He, We, res, S);
+    L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2);
+    L.coarse = make_plan(N, L.Hc, L.Wc, res, S);
     Carver c(ws);
-    w.rc = c.take<RenderConst>(N);
-    w.sin_t = c.take<float>(He);
-    w.cos_t = c.take<float>(He);
-    w.sin_p = c.take<float>(We);
-    w.cos_p = c.take<float>(We);
-    w.partial = c.take<float>(p.splits > 1 ? (size_t)p.splits * N * res * res * 3 : 1);
+    const size_t slice = (size_t)N * res * res * 3;
+    L.rc = c.take<RenderConst>(N);
+    L.sin_t = c.take<float>(He);
+    L.cos_t = c.take<float>(He);
+    L.sin_p = c.take<float>(We);
+    L.cos_p = c.take<float>(We);
+    L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
+    L.slab_raw = c.take<float>(slice * L.raw.splits);
+    L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
+    L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     return c.used();
 }
 
@@ -531,14 +629,66 @@ static void gauss_legendre(int S, float* x, float* w) {
     }
 }
 
+// footprint levels of a launch: power-of-two lattices below S when S is one of 2,4,8,16 (S^2 then divides the 256
+// threads); any other S runs as a single level
+static void set_levels(GatherArgs& g, int S, bool hierarchy) {
+    g.S = S;
+    g.nlev = 0;
+    const bool pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
+    if (hierarchy && pow2)
+        for (int sk = 1, ti = 0; sk < S; sk *= 2, ++ti) {
+            g.lev_S[g.nlev] = sk;
+            g.lev_tidx[g.nlev] = ti;
+            gauss_legendre(sk, g.gl_x[g.nlev], g.gl_w[g.nlev]);
+            ++g.nlev;
+        }
+    g.lev_S[g.nlev] = S;
+    g.lev_tidx[g.nlev] = MAX_LEVELS - 1;
+    gauss_legendre(S, g.gl_x[g.nlev], g.gl_w[g.nlev]);
+    ++g.nlev;
+}
+
+static int make_tensor_map(CUtensorMap* tmap, const float* base, int B, int Hm, int Wm, int floats_per_cell) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        set_error("render: cuTensorMapEncodeTiled entry point unavailable");
+        return DRM_ECUDA;
+    }
+    const cuuint64_t row = (cuuint64_t)Wm * floats_per_cell;
+    cuuint64_t dims[3] = {row, (cuuint64_t)Hm, (cuuint64_t)B};
+    cuuint64_t strides[2] = {row * 4, row * 4 * (cuuint64_t)Hm};
+    cuuint32_t box[3] = {(cuuint32_t)(TT * floats_per_cell), TT, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("render: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return DRM_ECUDA;
+    }
+    return DRM_OK;
+}
+
+template <int TERMS, bool COARSE_SRC>
+static int launch_gather(const GatherArgs& g, const CUtensorMap& tmap, const RenderPlan& p, int N, cudaStream_t st) {
+    const size_t raw_floats = (size_t)TILE_TEXELS * (COARSE_SRC ? COARSE_FLOATS : 3);
+    const size_t smem = 2 * raw_floats * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float) + 16 + 64 + MAX_LIST * 3;
+    DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<TERMS, COARSE_SRC>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.tiles_x * p.tiles_y, N, p.splits);
+    render_gather_kernel<TERMS, COARSE_SRC><<<grid, GATHER_THREADS, smem, st>>>(tmap, g);
+    count_launches(1);
+    return DRM_OK;
+}
+
 }  // namespace drm
 
 using namespace drm;
 
 extern "C" size_t drm_render_workspace_bytes(int N, int B, int He, int We, int res, int S) {
     if (N <= 0 || B <= 0 || He <= 0 || We <= 0 || res <= 0 || S < 1 || S > 16) return 0;
-    RenderWs w;
-    return render_carve(w, nullptr, N, He, We, res, make_plan(N, He, We, res, S));
+    RenderLayout L;
+    return render_layout(L, nullptr, N, B, He, We, res, S);
 }
 
 extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const int32_t* env_index, const float* z6,
@@ -550,84 +700,90 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     DRM_REQUIRE(S >= 1 && S <= 16, "render: footprint_S=%d not in 1..16", S);
     DRM_REQUIRE(res <= 4096, "render: res=%d too large", res);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    const RenderPlan p = make_plan(N, He, We, res, S);
-    RenderWs w;
-    const size_t need = render_carve(w, workspace, N, He, We, res, p);
+    RenderLayout L;
+    const size_t need = render_layout(L, workspace, N, B, He, We, res, S);
     if (!workspace || workspace_bytes < need) {
         set_error("render: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
         return DRM_EWORKSPACE;
     }
     if (!(alpha_min > 0.f)) alpha_min = fmaxf(1e-3f, (float)(1.25 * M_PI / He));
-
-    GatherArgs g{};
-    g.env = env; g.rc = w.rc; g.sin_t = w.sin_t; g.cos_t = w.cos_t; g.sin_p = w.sin_p; g.cos_p = w.cos_p;
-    g.out = out; g.partial = w.partial;
-    g.B = B; g.He = He; g.We = We; g.N = N; g.res = res; g.S = S;
-    g.tile_w = p.tile_w; g.tile_h = p.tile_h; g.tiles_x = p.tiles_x; g.tiles_y = p.tiles_y;
-    g.ttiles_x = p.ttiles_x; g.ttiles_y = p.ttiles_y; g.splits = p.splits;
-    g.channel_first = channel_first;
-    g.cull = 1;
-    g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
-    g.cell = (float)(M_PI / res);
-    // footprint levels: power-of-two lattices below S when S is one of 2,4,8,16 (S^2 then divides the 256 threads);
-    // any other S runs as a single level
-    g.nlev = 0;
-    const bool pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
-    const char* lv = getenv("DRM_RENDER_LEVELS");  // "0" disables the hierarchy (debugging / validation)
-    const bool hierarchy = pow2 && !(lv && lv[0] == '0');
-    if (hierarchy)
-        for (int sk = 1, ti = 0; sk < S; sk *= 2, ++ti) {
-            g.lev_S[g.nlev] = sk;
-            g.lev_tidx[g.nlev] = ti;
-            gauss_legendre(sk, g.gl_x[g.nlev], g.gl_w[g.nlev]);
-            ++g.nlev;
-        }
-    g.lev_S[g.nlev] = S;
-    g.lev_tidx[g.nlev] = MAX_LEVELS - 1;
-    gauss_legendre(S, g.gl_x[g.nlev], g.gl_w[g.nlev]);
-    ++g.nlev;
+    const char* lv = getenv("DRM_RENDER_LEVELS");  // "0" disables the footprint hierarchy (debugging / validation)
+    const bool hierarchy = !(lv && lv[0] == '0');
     float level_scale = 0.3f;  // thresholds of render_setup_kernel are conservative; 0.3 measured (scripts/levels_probe.py)
     if (const char* ls = getenv("DRM_RENDER_LEVEL_SCALE")) level_scale = (float)atof(ls);
 
-    // TMA descriptor over env viewed as [B][He][3*We] fp32; box = 32 rows x 96 floats of one map
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    g.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
-    if (g.use_tma) {
-        PFN_encodeTiled enc = get_encode_tiled();
-        if (!enc) {
-            set_error("render: cuTensorMapEncodeTiled entry point unavailable");
-            return DRM_ECUDA;
-        }
-        cuuint64_t dims[3] = {(cuuint64_t)We * 3, (cuuint64_t)He, (cuuint64_t)B};
-        cuuint64_t strides[2] = {(cuuint64_t)We * 12, (cuuint64_t)We * 12 * (cuuint64_t)He};
-        cuuint32_t box[3] = {TT * 3, TT, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(env), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("render: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-            return DRM_ECUDA;
-        }
-    }
+    GatherArgs g{};
+    g.rc = L.rc; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
+    g.B = B; g.He = He; g.We = We; g.N = N; g.res = res;
+    g.cull = 1;
+    g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
+    g.cell = (float)(M_PI / res);
 
     const int tb = 128;
-    render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(w.sin_t, w.cos_t, w.sin_p, w.cos_p, He, We);
-    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale, w.rc);
+    render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(L.sin_t, L.cos_t, L.sin_p, L.cos_p, He, We);
+    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale,
+                                                         L.coarse_enabled ? L.coarse_h : 0.f, L.coarse_diffuse_ok ? 1 : 0,
+                                                         L.rc);
+    count_launches(2);
+    if (L.coarse_enabled) {
+        const long cells = (long)B * L.Hc * L.Wc;
+        env_coarsen_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, B, He,
+                                                                            We, L.Hc, L.Wc, g.domega_k, L.coarse_map);
+        count_launches(1);
+    }
 
-    const size_t smem = 2 * RAW_FLOATS * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float) + 16 + 64 + MAX_LIST * 3;
-    DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(p.tiles_x * p.tiles_y, N, p.splits);
-    // both instantiations are launched; each CTA exits at once when its render belongs to the other one
-    render_gather_kernel<false><<<grid, GATHER_THREADS, smem, st>>>(tmap, g);
-    render_gather_kernel<true><<<grid, GATHER_THREADS, smem, st>>>(tmap, g);
-    if (p.splits > 1) {
+    auto fill_plan = [&](GatherArgs& a, const RenderPlan& p) {
+        a.tile_w = p.tile_w; a.tile_h = p.tile_h; a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y;
+        a.ttiles_x = p.ttiles_x; a.ttiles_y = p.ttiles_y; a.splits = p.splits;
+    };
+    int rc_code;
+    // ---- launches on the raw map: specular lobe only, and both lobes -------------------------------------------------
+    {
+        GatherArgs a = g;
+        a.src = env; a.Hm = He; a.Wm = We; a.slab = L.slab_raw;
+        a.dth_cell = (float)(M_PI / He); a.dph_cell = (float)(2.0 * M_PI / We);
+        fill_plan(a, L.raw);
+        set_levels(a, S, hierarchy);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        a.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
+        if (a.use_tma && (rc_code = make_tensor_map(&tmap, env, B, He, We, 3)) != DRM_OK) return rc_code;
+        a.route_mask = ROUTE_SPEC_RAW;
+        if ((rc_code = launch_gather<1, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
+        if (!L.coarse_diffuse_ok) {  // otherwise no render is routed to BOTH_RAW
+            a.route_mask = ROUTE_BOTH_RAW;
+            if ((rc_code = launch_gather<3, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
+        }
+    }
+    // ---- launches on the coarse map: diffuse lobe of the renders above, both lobes of the very rough renders --------
+    if (L.coarse_enabled) {
+        GatherArgs a = g;
+        a.src = L.coarse_map; a.Hm = L.Hc; a.Wm = L.Wc;
+        a.dth_cell = (float)(COARSE * M_PI / He); a.dph_cell = (float)(COARSE * 2.0 * M_PI / We);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        a.use_tma = ((L.Wc * COARSE_FLOATS * 4) % 16 == 0);
+        if (a.use_tma && (rc_code = make_tensor_map(&tmap, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS)) != DRM_OK) return rc_code;
+        if (L.coarse_diffuse_ok) {
+            a.slab = L.slab_diff; a.route_mask = ROUTE_DIFF_COARSE;
+            fill_plan(a, L.diff);
+            set_levels(a, L.diff.S, false);
+            if ((rc_code = launch_gather<2, true>(a, tmap, L.diff, N, st)) != DRM_OK) return rc_code;
+        }
+        a.slab = L.slab_coarse; a.route_mask = ROUTE_BOTH_COARSE;
+        fill_plan(a, L.coarse);
+        set_levels(a, S, hierarchy);
+        if ((rc_code = launch_gather<3, true>(a, tmap, L.coarse, N, st)) != DRM_OK) return rc_code;
+    }
+    {
+        SlabDesc s0{L.slab_raw, L.raw.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
+        SlabDesc s1{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff.splits, ROUTE_DIFF_COARSE};
+        SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
+        SlabDesc s3{nullptr, 0, 0};
         const size_t total = (size_t)N * res * res * 3;
-        render_reduce_splits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.partial, out, N, res, p.splits, channel_first);
+        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, L.rc, out, N, res, channel_first);
+        count_launches(1);
     }
     DRM_CHECK_CUDA(cudaGetLastError());
-    count_launches(4 + (p.splits > 1 ? 1 : 0));
     return DRM_OK;
 }

@@ -152,17 +152,21 @@ def test_dropin_class_statefulness_and_attributes():
 
 
 # ---- footprint hierarchy (coarser lattices for texel tiles far from the lobe) --------------------------------------
-def _with_levels(flag, fn):
+def _with_env(name, flag, fn):
     import os
-    old = os.environ.get("DRM_RENDER_LEVELS")
-    os.environ["DRM_RENDER_LEVELS"] = flag
+    old = os.environ.get(name)
+    os.environ[name] = flag
     try:
         return fn()
     finally:
         if old is None:
-            os.environ.pop("DRM_RENDER_LEVELS", None)
+            os.environ.pop(name, None)
         else:
-            os.environ["DRM_RENDER_LEVELS"] = old
+            os.environ[name] = old
+
+
+def _with_levels(flag, fn):
+    return _with_env("DRM_RENDER_LEVELS", flag, fn)
 
 
 @pytest.mark.parametrize("case", [("z0_mirror", 16), ("near_mirror_schedule", 16), ("glossy_metal", 4), ("mixed", 2)])
@@ -194,3 +198,24 @@ def test_hierarchy_parity_vs_oracle_windows(zname):
         ref = render_oracle(env, z, VIEWS[0], 128, S=16, window=win)
         a, b = ours[win[0]:win[1], win[2]:win[3]], ref[win[0]:win[1], win[2]:win[3]]
         assert rel_l2(a, b) <= TOL, (zname, win, rel_l2(a, b))
+
+
+# ---- coarse-map routes (diffuse lobe / very rough specular lobe gathered from the 4x4 energy-centroid map) ----------
+@pytest.mark.parametrize("zname,S", [("rough_dielectric", 1), ("mixed", 2), ("random7", 2)])
+def test_coarse_routes_match_raw_map_full_size(zname, S):
+    """2000x1000 -> 128x128, all pixels: routes through the coarse map against everything gathered from the raw map."""
+    env = synthetic_envmap(1000, 2000, seed=1004, device=DEV)[None]
+    z = torch.tensor([Z_CASES[zname]])
+    v = torch.tensor([VIEWS[1]])
+    fast = render_batch(env, z, v, res=128, footprint_S=S)
+    full = _with_env("DRM_RENDER_COARSE", "0", lambda: _with_levels("0", lambda: render_batch(env, z, v, res=128, footprint_S=S)))
+    torch.cuda.synchronize()
+    assert rel_l2(fast.cpu().numpy(), full.cpu().numpy()) <= 7e-5
+
+
+@pytest.mark.parametrize("z", [[0.2, 0.9, 0.8, 0.7, 0.85, 0.6], [0.0, 1.0, 1.0, 1.0, 0.3, 0.0], [1.0, 0.9, 0.5, 0.3, 1.0, 1.0]])
+def test_coarse_routes_parity_vs_oracle_full_size(z):
+    """Very rough (both lobes from the coarse map), diffuse-dominated (diffuse from the coarse map), rough metal."""
+    env = synthetic_envmap(1000, 2000, seed=1007)
+    ours = _render(env[None], [z], [VIEWS[3]], 16, 1, channel_first=False)[0]
+    assert rel_l2(ours, render_oracle(env, z, VIEWS[3], 16, S=1)) <= TOL
