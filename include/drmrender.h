@@ -12,6 +12,8 @@
  *                              and the per-render Python loops that call it  models/drmnet.py:561-569, :680-691
  *   drm_img2refmap          <- refmap_mask_make()                        utils/img2refmap.py:6-37
  *                              (+ xyz2thetaphi as called there             utils/transform.py:55-89)
+ *   drm_refmap_postprocess  <- luminance normalisation + log transform   models/drmnet.py:610-620, dataset/basedataset.py:52-53
+ *   drm_mirmap2envmap       <- mirmap2envmap() inside DRMNet.r0toenvmap   utils/transform.py:106-144, models/drmnet.py:931-941
  */
 #ifndef DRMRENDER_H
 #define DRMRENDER_H
@@ -78,6 +80,23 @@ int drm_img2refmap(const float* colors, const float* normals_or_thetaphi, int in
                    const int64_t* offsets, int64_t total_n, int B, int C, int res, float thr, int min_points,
                    int reduce_mode, float* refmap, uint8_t* refmask, int32_t* counts, int32_t* sel_index,
                    void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Callers either side of the render.
+ *
+ * drm_refmap_postprocess: in/out [G, N, 3, res, res] fp32 (stack 0 = LrK).  target > 0: every stack of sample n is
+ *   multiplied by target / geometric-mean luminance of LrK[n] over L > 0 (models/drmnet.py:610-617; 0.12 in the shipped
+ *   configs), scale_out [N] receives the factor (may be NULL).  transform 1 applies log10(x + 0.1) + 1
+ *   (dataset/basedataset.py:52-53), 0 none.  in may equal out.
+ * drm_mirmap2envmap: mirror refmap [B, C, H, W] -> lat-long envmap [B, C, OH, OW] with the defaults of
+ *   utils/transform.py:106-144 (view (0,0,1), bilinear, border); basis [C, H, W] (may be NULL) divides the refmap first
+ *   (DRMNet.r0toenvmap, models/drmnet.py:939-940).
+ * ------------------------------------------------------------------------------------------------------------- */
+int drm_refmap_postprocess(const float* in, int G, int N, int res, float target, int transform,
+                           float* scale_out, float* out, void* cuda_stream);
+
+int drm_mirmap2envmap(const float* mirmap, const float* basis, int B, int C, int H, int W, int OH, int OW,
+                      float* out, void* cuda_stream);
 
 /* angles only: [n,3] normals -> [n,2] (theta, phi), the arithmetic of utils/transform.py:84-89 at img2refmap.py:20 */
 int drm_normals_to_thetaphi(const float* normals, int64_t n, float* thetaphi, void* cuda_stream);

@@ -1,0 +1,50 @@
+"""CPU oracles for the callers either side of the render.  TEST INFRASTRUCTURE ONLY.
+
+* ``postprocess_oracle`` restates models/drmnet.py:610-620 + dataset/basedataset.py:52-53 (float64).
+* ``mirmap2envmap_oracle`` restates utils/transform.py:106-144 (defaults) + torch.nn.functional.grid_sample
+  (bilinear, padding_mode="border", align_corners=False) in float64; pinned by tests/golden/mirmap_ref.npz, which holds
+  the reference's own output.
+"""
+import numpy as np
+
+
+def postprocess_oracle(stacks, target=0.12, transform="log"):
+    x = np.asarray(stacks, dtype=np.float64)
+    G, N = x.shape[:2]
+    scale = np.ones(N)
+    if target:
+        r = x[0]
+        L = 0.212671 * r[:, 0] + 0.715160 * r[:, 1] + 0.072169 * r[:, 2]
+        m = L > 0
+        Lmean = np.exp((np.log(np.clip(L, 1e-5, None)) * m).sum((1, 2)) / m.sum((1, 2)))
+        scale = target / Lmean
+    y = x * scale[None, :, None, None, None]
+    if transform == "log":
+        y = np.log10(y + 0.1) + 1
+    return y, scale
+
+
+def mirmap2envmap_oracle(mirmap, output_shape, basis=None):
+    m = np.asarray(mirmap, dtype=np.float64)
+    if basis is not None:
+        m = m / np.asarray(basis, dtype=np.float64)[None]
+    B, C, H, W = m.shape
+    OH, OW = output_shape
+    theta = (np.arange(OH) + 0.5) * (np.pi / OH)
+    phi = -(np.arange(OW) + 0.5) * (2 * np.pi / OW)
+    th, ph = np.meshgrid(theta, phi, indexing="ij")
+    # thetaphi2xyz(normal=[0,1,0], tangent=[0,0,-1]) -> binormal [-1,0,0]
+    xyz = np.stack([-np.sin(th) * np.sin(ph), np.cos(th), -np.sin(th) * np.cos(ph)], -1)
+    h = xyz + np.array([0.0, 0.0, 1.0])
+    h = h / np.clip(np.linalg.norm(h, axis=-1, keepdims=True), 1e-12, None)
+    t_h = np.arccos(np.clip(h[..., 1], -1, 1))
+    p_h = np.arctan2(h[..., 0], h[..., 2])
+    u, v = p_h * (2 / np.pi), t_h * (2 / np.pi) - 1
+    ix = np.clip(((u + 1) * W - 1) / 2, 0, W - 1)
+    iy = np.clip(((v + 1) * H - 1) / 2, 0, H - 1)
+    x0, y0 = np.floor(ix).astype(int), np.floor(iy).astype(int)
+    wx, wy = ix - x0, iy - y0
+    x1, y1 = np.minimum(x0 + 1, W - 1), np.minimum(y0 + 1, H - 1)  # weight is 0 whenever the clamp is active
+    out = (m[:, :, y0, x0] * (1 - wx) * (1 - wy) + m[:, :, y0, x1] * wx * (1 - wy)
+           + m[:, :, y1, x0] * (1 - wx) * wy + m[:, :, y1, x1] * wx * wy)
+    return out

@@ -34,7 +34,7 @@ def test_version_and_error_string(lib):
 
 def test_workspace_queries(lib):
     assert lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1) > 0
-    assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 1) > lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1)
+    assert lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1) > lib.drm_render_workspace_bytes(64, 1, 1000, 2000, 128, 1)
     assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 17) == 0
     assert lib.drm_render_workspace_bytes(0, 1, 1000, 2000, 128, 1) == 0
     a = lib.drm_img2refmap_workspace_bytes(27774, 1, 128, 3.14159 / 256)

@@ -1,0 +1,29 @@
+"""Pin the oracles of the 'next' rows (N1 post-processing, N2 mirmap2envmap) on CPU."""
+import numpy as np
+import torch
+
+from oracle.callers_oracle import mirmap2envmap_oracle, postprocess_oracle
+
+
+def test_mirmap2envmap_oracle_matches_reference_output(golden_mirmap):
+    """golden: the reference's mirmap2envmap (utils/transform.py:106-144) on its own envmap2mirmap output."""
+    mir = golden_mirmap["mirmap_v001"].transpose(2, 0, 1)[None]
+    ours = mirmap2envmap_oracle(mir, (32, 64))[0].transpose(1, 2, 0)
+    ref = golden_mirmap["envmap_from_mirmap_v001"]
+    assert np.abs(ours - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_postprocess_oracle_matches_torch_formulas():
+    """The same expressions evaluated with torch ops (models/drmnet.py:610-620, dataset/basedataset.py:52-53)."""
+    g = torch.Generator().manual_seed(0)
+    stacks = torch.rand(3, 4, 3, 16, 16, generator=g) * 3
+    stacks[0, 1, :, :4] = 0  # L == 0 pixels are excluded from the mean
+    LrK = stacks[0]
+    L = 0.212671 * LrK[:, 0] + 0.715160 * LrK[:, 1] + 0.072169 * LrK[:, 2]
+    m = L > 0
+    Lmean = torch.exp((torch.log(L.clip(1e-5)) * m).sum(dim=(1, 2)) / m.sum(dim=(1, 2)))
+    scale = 0.12 / Lmean
+    ref = torch.log10(stacks * scale[None, :, None, None, None] + 1e-1) + 1
+    ours, s = postprocess_oracle(stacks.numpy())
+    assert np.allclose(s, scale.numpy(), rtol=1e-5)
+    assert np.allclose(ours, ref.numpy(), rtol=1e-5, atol=1e-6)
