@@ -183,6 +183,14 @@ int drm_oracle_render_records(const double* rec_dir, const double* rec_E, long T
     return 0;
 }
 
+void drm_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int drm_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -51,6 +51,11 @@ def num_threads() -> int:
     return int(_load().drm_oracle_num_threads())
 
 
+def set_threads(n: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for all host cores explicitly."""
+    _load().drm_oracle_set_threads(int(n))
+
+
 def z_from_named(z, names) -> np.ndarray:
     """Scene defaults (mitsuba3_utils.py:348-361) overridden by the named entries, clipped to [0,1] (:237-242)."""
     out = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 1.0])
