@@ -39,6 +39,11 @@ static constexpr int MAX_LEVELS = 5;   // footprint lattices 1,2,4,8,16 per axis
 static constexpr int MAX_LIST = 2048;  // tiles one CTA can schedule (the plan splits larger maps)
 static constexpr int COARSE = 4;       // coarsening factor of the energy-centroid map
 static constexpr int COARSE_FLOATS = 6;  // centroid direction + radiance * solid angle per coarse cell
+static constexpr int FAR_EDGE = 16;     // cells per side of the far launch's blocks
+
+// A launch pair splits the (cell, tile) plane: the far launch takes, with large blocks of cells and the 1x1 lattice,
+// every tile that is far (1x1-accurate) from the whole block; the near launch takes the rest with small blocks.
+enum : int { PART_ALL = 0, PART_FAR = 1, PART_NEAR = 2 };
 
 // which launch serves which part of a render
 enum : int { ROUTE_SPEC_RAW = 1, ROUTE_BOTH_RAW = 2, ROUTE_DIFF_COARSE = 4, ROUTE_BOTH_COARSE = 8 };
@@ -61,6 +66,9 @@ struct GatherArgs {
     int tile_w, tile_h, tiles_x, tiles_y;
     int ttiles_x, ttiles_y, splits;
     int use_tma, cull, route_mask;
+    int G;                     // sub-normal slots per refmap cell (a multiple of S*S)
+    int part;                  // PART_ALL, or the far / near half of a launch pair (see far_tile)
+    int far_edge;              // edge, in cells, of the blocks the far launch works on
     int nlev;                  // number of footprint levels used by this launch
     int lev_S[MAX_LEVELS];     // lattice size per axis of level k (ascending; the last one is S)
     int lev_tidx[MAX_LEVELS];  // log2(lev_S[k]): index into RenderConst::thr
@@ -185,13 +193,26 @@ __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
     return 0.5f * (a_s * a_s + a_p * a_p);
 }
 
-// Classify one map tile for a CTA whose normals lie in the cone (axis a, radius beta):
-//   0      no normal of the cone sees any direction of the tile (n.d <= 0 everywhere): skipped
-//   1+k    footprint level k (0 = 1x1 lattice ... nlev-1 = full S x S lattice) chosen from the distance, in
-//          half-vector space, between the cone of normals and the tile's half vectors h = normalize(v + d)
-__device__ __forceinline__ int classify_tile(const GatherArgs& g, const float* __restrict__ vhat,
-                                             const float* __restrict__ thr, int tile, float ax, float ay, float az,
-                                             float beta) {
+// Cone (axis, angular radius) of the normals of the cells [i0,i1) x [j0,j1), cell corners included.
+__device__ __forceinline__ void cell_block_cone(const GatherArgs& g, const RenderConst& rc, int i0, int i1, int j0,
+                                                int j1, float& ax, float& ay, float& az, float& beta) {
+    const float thc = 0.5f * (i0 + i1) * g.cell, phc = 0.5f * (j0 + j1) * g.cell;
+    float st, ct, sp, cp;
+    sincosf(thc, &st, &ct);
+    sincosf(phc, &sp, &cp);
+    const float lx = st * cp, lz = st * sp;
+    ax = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
+    ay = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
+    az = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
+    const float dth = 0.5f * (i1 - i0) * g.cell, dph = 0.5f * (j1 - j0) * g.cell;
+    beta = dth + dph * fminf(1.f, st + dth);
+}
+
+// Distance, in half-vector space, between a cone of normals and the half vectors h = normalize(v + d) of one map tile;
+// -1 when no normal of the cone sees any direction of the tile (n.d <= 0 everywhere), -0.5 when the d -> h map is
+// singular over the tile (d ~ -v) and no bound is available.
+__device__ __forceinline__ float tile_distance(const GatherArgs& g, const float* __restrict__ vhat, int tile, float ax,
+                                               float ay, float az, float beta) {
     const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
     const int r0 = ty * TT, r1 = min(r0 + TT, g.Hm), c0 = tx * TT, c1 = min(c0 + TT, g.Wm);
     const float dth = 0.5f * (r1 - r0) * g.dth_cell, dph = 0.5f * (c1 - c0) * g.dph_cell;
@@ -204,15 +225,37 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const float* _
     const float dx = st * sp, dy = ct, dz = -st * cp;
     if (g.cull) {
         const float spread = beta + gamma + 0.01f;
-        if (spread < 1.5607963f && ax * dx + ay * dy + az * dz <= -sinf(spread)) return 0;
+        if (spread < 1.5607963f && ax * dx + ay * dy + az * dz <= -sinf(spread)) return -1.f;
     }
-    if (g.nlev == 1) return 1;
     const float hx = vhat[0] + dx, hy = vhat[1] + dy, hz = vhat[2] + dz;
     const float len = sqrtf(hx * hx + hy * hy + hz * hz);
-    if (len - gamma < 0.05f) return g.nlev;  // d ~ -v: the d -> h map is singular, stay on the finest lattice
+    if (len - gamma < 0.05f) return -0.5f;
     const float gamma_h = gamma / (len - gamma);  // |dh| <= |dd| / |v + d|
     const float cosang = fminf(fmaxf((ax * hx + ay * hy + az * hz) / len, -1.f), 1.f);
-    const float dist = acosf(cosang) - beta - gamma_h;
+    return fmaxf(acosf(cosang) - beta - gamma_h, 0.f);
+}
+
+// Classify one map tile for the CTA whose cells are [pi0,pi1) x [pj0,pj1):
+//   0      skipped (invisible, or it belongs to the other launch of a far/near pair)
+//   1+k    footprint level k (0 = 1x1 lattice ... nlev-1 = full S x S lattice)
+__device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderConst& rcs, const float* __restrict__ vhat,
+                                             const float* __restrict__ thr, int tile, int pi0, int pi1, int pj0, int pj1,
+                                             float ax, float ay, float az, float beta) {
+    if (g.part != PART_ALL) {
+        // the far block enclosing (or equal to) my cells decides, identically in both launches of the pair
+        const int e = g.far_edge;
+        const int fi0 = (pi0 / e) * e, fj0 = (pj0 / e) * e;
+        float fx, fy, fz, fb;
+        cell_block_cone(g, rcs, fi0, min(fi0 + e, g.res), fj0, min(fj0 + e, g.res), fx, fy, fz, fb);
+        const float fd = tile_distance(g, vhat, tile, fx, fy, fz, fb);
+        const bool is_far = fd >= thr[0];
+        if (g.part == PART_FAR) return (fd >= 0.f || fd == -0.5f) && is_far ? 1 : 0;
+        if (is_far || fd == -1.f) return 0;  // far: the other launch; invisible from the big block: from mine too
+    }
+    const float dist = tile_distance(g, vhat, tile, ax, ay, az, beta);
+    if (dist == -1.f) return 0;
+    if (g.nlev == 1) return 1;
+    if (dist == -0.5f) return g.nlev;  // no bound: stay on the finest lattice
     for (int k = 0; k < g.nlev - 1; ++k)
         if (dist >= thr[g.lev_tidx[k]]) return 1 + k;
     return g.nlev;
@@ -242,24 +285,13 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     const int ptile = blockIdx.x;
     const int pty = ptile / g.tiles_x, ptx = ptile - pty * g.tiles_x;
     const int pi0 = pty * g.tile_h, pj0 = ptx * g.tile_w;
-    const int S2 = g.S * g.S;
+    const int G = g.G;  // slots per cell
     const int npix = g.tile_w * g.tile_h;
 
     // ---- cone of this CTA's normals (cell corners included) ---------------------------------------------------------
+    const int pi1 = min(pi0 + g.tile_h, g.res), pj1 = min(pj0 + g.tile_w, g.res);
     float ax, ay, az, beta;
-    {
-        const int i1 = min(pi0 + g.tile_h, g.res), j1 = min(pj0 + g.tile_w, g.res);
-        const float thc = 0.5f * (pi0 + i1) * g.cell, phc = 0.5f * (pj0 + j1) * g.cell;
-        float st, ct, sp, cp;
-        sincosf(thc, &st, &ct);
-        sincosf(phc, &sp, &cp);
-        const float lx = st * cp, lz = st * sp;
-        ax = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
-        ay = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
-        az = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
-        const float dth = 0.5f * (i1 - pi0) * g.cell, dph = 0.5f * (j1 - pj0) * g.cell;
-        beta = dth + dph * fminf(1.f, st + dth);
-    }
+    cell_block_cone(g, rc, pi0, pi1, pj0, pj1, ax, ay, az, beta);
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -275,7 +307,8 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     const int tbeg = blockIdx.z, tstep = g.splits;
     const int nmine = (ntiles - tbeg + tstep - 1) / tstep;
     for (int e = tid; e < nmine; e += GATHER_THREADS)
-        lvl[e] = (uint8_t)classify_tile(g, g.rc[k].vhat, g.rc[k].thr, tbeg + e * tstep, ax, ay, az, beta);
+        lvl[e] = (uint8_t)classify_tile(g, rc, g.rc[k].vhat, g.rc[k].thr, tbeg + e * tstep, pi0, pi1, pj0, pj1, ax, ay, az,
+                                        beta);
     __syncthreads();
     int nlist = 0;
     {
@@ -331,24 +364,24 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     }
 
     // ---- per-level state of my 4 slots: lattice node, texel subset, normals -----------------------------------------
-    // slot q = r*256 + tid -> pixel q / S^2, sub = q % S^2.  At a level with an Sk x Sk lattice the S^2 slots of a
-    // pixel form Sk^2 groups of gk = (S/Sk)^2 slots: the group evaluates one lattice node, its gk slots split the tile's
-    // texels (t = u, u+gk, ...).  S^2 divides 256, so the 4 slots of a thread share node and subset.
+    // slot q = r*256 + tid -> cell q / G, sub = q % G (G slots per cell, a multiple of S^2).  At a level with an
+    // Sk x Sk lattice the G slots of a cell form Sk^2 groups of gk = G / Sk^2 slots: the group evaluates one lattice
+    // node, its gk slots split the tile's texels (t = u, u+gk, ...).  G divides 256, so the 4 slots of a thread share
+    // node and subset.
     float nx[SUBS_PER_THREAD], ny[SUBS_PER_THREAD], nz[SUBS_PER_THREAD], nv[SUBS_PER_THREAD];
     float Fi[SUBS_PER_THREAD], mult[SUBS_PER_THREAD], wq[SUBS_PER_THREAD];
     int cur_level = 0, level_end = 0, gk = 1, u0 = 0;
-    const bool hier = (GATHER_THREADS % S2) == 0;
+    const bool hier = (GATHER_THREADS % G) == 0;
 
     for (int it = 0; it < nlist; ++it) {
         if (it >= level_end) {
             do { ++cur_level; level_end = scan_ws[8 + cur_level]; } while (it >= level_end);  // next non-empty level
             const int Sk = g.lev_S[cur_level - 1];
-            const int ratio = g.S / Sk;
-            gk = hier ? ratio * ratio : 1;
+            gk = hier ? G / (Sk * Sk) : 1;
 #pragma unroll
             for (int r = 0; r < SUBS_PER_THREAD; ++r) {
                 const int q = r * GATHER_THREADS + tid;
-                const int pl = q / S2, sub = q - pl * S2;
+                const int pl = q / G, sub = q - pl * G;
                 const int li = pl / g.tile_w, lj = pl - li * g.tile_w;
                 const int i = pi0 + li, j = pj0 + lj;
                 const int node = sub / gk;
@@ -514,7 +547,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
         const int i = pi0 + li, j = pj0 + lj;
         if (i >= g.res || j >= g.res) continue;
         float v = 0.f;
-        for (int s2 = 0; s2 < S2; ++s2) v += resbuf[(pl * S2 + s2) * 3 + c];
+        for (int s2 = 0; s2 < G; ++s2) v += resbuf[(pl * G + s2) * 3 + c];
         const size_t pix = (size_t)i * g.res + j;
         g.slab[(((size_t)blockIdx.z * g.N + k) * g.res * g.res + pix) * 3 + c] = v;
     }
@@ -547,13 +580,18 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
 }
 
 struct RenderPlan {
-    int S, tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
+    int S, G, tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
 };
 
-static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S) {
+// slots per cell: S^2, raised to 16 for the 2x2 and 4x4 lattices so that their blocks are 8x8 cells (a tighter cone of
+// normals sends more tiles to the coarse levels)
+static int default_slots(int S) { return (S == 2 || S == 4) ? 16 : S * S; }
+
+static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
     RenderPlan p;
     p.S = S;
-    int px = SLOTS / (S * S);
+    p.G = G;
+    int px = SLOTS / G;
     int e = (int)floor(sqrt((double)px));
     if (e < 1) e = 1;
     if (e > res) e = res;
@@ -579,9 +617,10 @@ struct RenderLayout {
     int Hc, Wc;
     bool coarse_enabled, coarse_diffuse_ok;
     float coarse_h;
-    RenderPlan raw, diff, coarse;  // launches: spec/both on the raw map, diffuse on the coarse map, both on the coarse map
+    bool far_pair;  // the raw-map launch is split into a far launch (16x16-cell blocks) and a near launch
+    RenderPlan raw, far, diff, coarse;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse map
     RenderConst* rc;
-    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *slab_raw, *slab_diff, *slab_coarse;
+    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *slab_raw, *slab_far, *slab_diff, *slab_coarse;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -591,9 +630,11 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     const char* cv = getenv("DRM_RENDER_COARSE");  // "0" disables the coarse-map routes (debugging / validation)
     L.coarse_enabled = !(cv && cv[0] == '0') && He >= 8 * COARSE && We >= 8 * COARSE;
     L.coarse_diffuse_ok = L.coarse_enabled && L.coarse_h <= 0.0135f;
-    L.raw = make_plan(N, He, We, res, S);
-    L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2);
-    L.coarse = make_plan(N, L.Hc, L.Wc, res, S);
+    L.far_pair = (S == 8 || S == 16) && res >= FAR_EDGE;
+    L.raw = make_plan(N, He, We, res, S, default_slots(S));
+    L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE));
+    L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2));
+    L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S));
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -603,6 +644,7 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.cos_p = c.take<float>(We);
     L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
     L.slab_raw = c.take<float>(slice * L.raw.splits);
+    L.slab_far = c.take<float>(L.far_pair ? slice * L.far.splits : 1);
     L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     return c.used();
@@ -716,6 +758,8 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     g.rc = L.rc; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
     g.B = B; g.He = He; g.We = We; g.N = N; g.res = res;
     g.cull = 1;
+    g.part = PART_ALL;
+    g.far_edge = FAR_EDGE;
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
     g.cell = (float)(M_PI / res);
 
@@ -735,8 +779,10 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     auto fill_plan = [&](GatherArgs& a, const RenderPlan& p) {
         a.tile_w = p.tile_w; a.tile_h = p.tile_h; a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y;
         a.ttiles_x = p.ttiles_x; a.ttiles_y = p.ttiles_y; a.splits = p.splits;
+        a.G = p.G;
     };
     int rc_code;
+    bool used_far = false;
     // ---- launches on the raw map: specular lobe only, and both lobes -------------------------------------------------
     {
         GatherArgs a = g;
@@ -748,12 +794,28 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         memset(&tmap, 0, sizeof(tmap));
         a.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
         if (a.use_tma && (rc_code = make_tensor_map(&tmap, env, B, He, We, 3)) != DRM_OK) return rc_code;
+        const bool pair = L.far_pair && hierarchy;
+        a.part = pair ? PART_NEAR : PART_ALL;
         a.route_mask = ROUTE_SPEC_RAW;
         if ((rc_code = launch_gather<1, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
         if (!L.coarse_diffuse_ok) {  // otherwise no render is routed to BOTH_RAW
             a.route_mask = ROUTE_BOTH_RAW;
             if ((rc_code = launch_gather<3, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
         }
+        if (pair) {
+            // far half: 16x16-cell blocks, 1x1 lattice, 4 slots per cell share each tile's texels
+            GatherArgs f = a;
+            f.part = PART_FAR; f.slab = L.slab_far;
+            fill_plan(f, L.far);
+            set_levels(f, 1, false);
+            f.route_mask = ROUTE_SPEC_RAW;
+            if ((rc_code = launch_gather<1, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            if (!L.coarse_diffuse_ok) {
+                f.route_mask = ROUTE_BOTH_RAW;
+                if ((rc_code = launch_gather<3, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            }
+        }
+        used_far = pair;
     }
     // ---- launches on the coarse map: diffuse lobe of the renders above, both lobes of the very rough renders --------
     if (L.coarse_enabled) {
@@ -779,7 +841,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         SlabDesc s0{L.slab_raw, L.raw.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
         SlabDesc s1{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff.splits, ROUTE_DIFF_COARSE};
         SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
-        SlabDesc s3{nullptr, 0, 0};
+        SlabDesc s3{used_far ? L.slab_far : nullptr, L.far.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
         const size_t total = (size_t)N * res * res * 3;
         render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, L.rc, out, N, res, channel_first);
         count_launches(1);
