@@ -37,7 +37,8 @@ static constexpr int TILE_TEXELS = TT * TT;
 static constexpr int REC_FLOATS = 12;
 static constexpr int MAX_LEVELS = 5;   // footprint lattices 1,2,4,8,16 per axis
 static constexpr int MAX_LIST = 2048;  // tiles one CTA can schedule (the plan splits larger maps)
-static constexpr int COARSE = 4;       // coarsening factor of the energy-centroid map
+static constexpr int COARSE = 4;       // coarsening factor of the energy-centroid map (diffuse lobe, very rough lobes)
+static constexpr int COARSE2 = 2;      // finer coarsening for moderately rough specular lobes
 static constexpr int COARSE_FLOATS = 6;  // centroid direction + radiance * solid angle per coarse cell
 static constexpr int FAR_EDGE = 16;     // cells per side of the far launch's blocks
 
@@ -46,7 +47,7 @@ static constexpr int FAR_EDGE = 16;     // cells per side of the far launch's bl
 enum : int { PART_ALL = 0, PART_FAR = 1, PART_NEAR = 2 };
 
 // which launch serves which part of a render
-enum : int { ROUTE_SPEC_RAW = 1, ROUTE_BOTH_RAW = 2, ROUTE_DIFF_COARSE = 4, ROUTE_BOTH_COARSE = 8 };
+enum : int { ROUTE_SPEC_RAW = 1, ROUTE_BOTH_RAW = 2, ROUTE_DIFF_COARSE = 4, ROUTE_BOTH_COARSE = 8, ROUTE_BOTH_COARSE2 = 16 };
 
 struct RenderConst {  // per render
     float vhat[3], left[3], upp[3];  // camera frame of look_at(v, 0, +Y); `left` carries the flip sign
@@ -90,24 +91,24 @@ __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, f
     }
 }
 
-// K3: 4x4-texel energy-centroid coarsening.  Cell = {unit centroid direction (luminance * solid-angle weighted),
+// K3: F x F-texel energy-centroid coarsening (F = 4 and 2).  Cell = {unit centroid direction (luminance * solid-angle weighted),
 // sum of radiance * solid angle per channel}: placing the cell's energy at its centroid cancels the first-order error
 // of evaluating a smooth lobe once per cell.
 __global__ void env_coarsen_kernel(const float* __restrict__ env, const float* __restrict__ sin_t,
                                    const float* __restrict__ cos_t, const float* __restrict__ sin_p,
-                                   const float* __restrict__ cos_p, int B, int He, int We, int Hc, int Wc,
+                                   const float* __restrict__ cos_p, int B, int He, int We, int Hc, int Wc, int F,
                                    float domega_k, float* __restrict__ coarse) {
     const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (cell >= (long)B * Hc * Wc) return;
     const int C = (int)(cell % Wc), R = (int)((cell / Wc) % Hc), b = (int)(cell / ((long)Wc * Hc));
     const float* src = env + (size_t)b * He * We * 3;
     float m0 = 0.f, m1 = 0.f, m2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for (int dr = 0; dr < COARSE; ++dr) {
-        const int r = R * COARSE + dr;
+    for (int dr = 0; dr < F; ++dr) {
+        const int r = R * F + dr;
         if (r >= He) break;
         const float st = sin_t[r], ct = cos_t[r], dom = domega_k * st;
-        for (int dc = 0; dc < COARSE; ++dc) {
-            const int c = C * COARSE + dc;
+        for (int dc = 0; dc < F; ++dc) {
+            const int c = C * F + dc;
             if (c >= We) break;
             const float* e = src + ((size_t)r * We + c) * 3;
             const float er = e[0] * dom, eg = e[1] * dom, eb = e[2] * dom;
@@ -131,7 +132,7 @@ __global__ void env_coarsen_kernel(const float* __restrict__ env, const float* _
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N,
                                     int B, float alpha_min, float cell, float level_scale, float coarse_h,
-                                    int coarse_diffuse_ok, RenderConst* __restrict__ rc) {
+                                    float coarse2_h, int coarse_diffuse_ok, RenderConst* __restrict__ rc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     RenderConst c;
@@ -159,10 +160,13 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
-    // routing: measured error of one evaluation per 4x4 cell ~ 0.03 (h/alpha)^2 for the GGX lobe and ~ 0.18 h^2 for the
-    // diffuse lobe (h = cell size in radians, oracle study in DESIGN.md); each is held near 2-3e-5
-    const bool spec_coarse = coarse_h > 0.f && coarse_h <= 0.026f * alpha;
+    // routing: the error of one evaluation per coarse cell of size h is ~ 0.03 (h/alpha)^2 for the GGX lobe on smooth
+    // skies and up to ~ 6e-6 / alpha^2 for a compact sun inside a cell (its extent is lost), ~ 0.18 h^2 for the diffuse
+    // lobe (oracle and scripts/coarse_probe.py studies); h <= 0.018 alpha holds the worst map near 5e-5
+    const bool spec_coarse = coarse_h > 0.f && coarse_h <= 0.018f * alpha;
+    const bool spec_coarse2 = coarse2_h > 0.f && coarse2_h <= 0.018f * alpha;
     if (spec_coarse) c.route = ROUTE_BOTH_COARSE;
+    else if (spec_coarse2) c.route = ROUTE_BOTH_COARSE2;
     else if (!has_diffuse) c.route = ROUTE_SPEC_RAW;
     else c.route = coarse_diffuse_ok ? (ROUTE_SPEC_RAW | ROUTE_DIFF_COARSE) : ROUTE_BOTH_RAW;
     float vx = view3[3 * k], vy = view3[3 * k + 1], vz = view3[3 * k + 2];
@@ -204,8 +208,9 @@ __device__ __forceinline__ void cell_block_cone(const GatherArgs& g, const Rende
     ax = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
     ay = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
     az = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
-    const float dth = 0.5f * (i1 - i0) * g.cell, dph = 0.5f * (j1 - j0) * g.cell;
-    beta = dth + dph * fminf(1.f, st + dth);
+    // angular radius: centre-to-corner distance d obeys d^2 <= dth^2 + (dph sin_max)^2 (5 % margin)
+    const float dth = 0.5f * (i1 - i0) * g.cell, dph = 0.5f * (j1 - j0) * g.cell * fminf(1.f, st + dth);
+    beta = 1.05f * sqrtf(dth * dth + dph * dph);
 }
 
 // Distance, in half-vector space, between a cone of normals and the half vectors h = normalize(v + d) of one map tile;
@@ -220,8 +225,9 @@ __device__ __forceinline__ float tile_distance(const GatherArgs& g, const float*
     float st, ct, sp, cp;
     sincosf(thc, &st, &ct);
     sincosf(phc, &sp, &cp);
-    // angular radius of the tile: meridian move + parallel move (the arc on the parallel bounds the great-circle one)
-    const float gamma = dth + dph * fminf(1.f, st + dth);
+    // angular radius of the tile: centre-to-corner distance d obeys d^2 <= dth^2 + (dph sin_max)^2 (5 % margin)
+    const float dps = dph * fminf(1.f, st + dth);
+    const float gamma = 1.05f * sqrtf(dth * dth + dps * dps);
     const float dx = st * sp, dy = ct, dz = -st * cp;
     if (g.cull) {
         const float spread = beta + gamma + 0.01f;
@@ -559,7 +565,7 @@ struct SlabDesc {
 };
 
 // out = sum over the launches that served the render and over their texel splits, in fixed order (deterministic)
-__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3,
+__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4,
                                       const RenderConst* __restrict__ rc, float* __restrict__ out, int N, int res,
                                       int channel_first) {
     const size_t total = (size_t)N * res * res * 3;
@@ -570,9 +576,9 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
     const size_t k = o / 3 / ((size_t)res * res);
     const int route = rc[k].route;
     float v = 0.f;
-    const SlabDesc slabs[4] = {s0, s1, s2, s3};
+    const SlabDesc slabs[5] = {s0, s1, s2, s3, s4};
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
+    for (int l = 0; l < 5; ++l)
         if (slabs[l].base && (route & slabs[l].route_mask))
             for (int s = 0; s < slabs[l].splits; ++s) v += slabs[l].base[(size_t)s * total + o];
     const size_t idx = channel_first ? (k * 3 + c) * res * res + pix : o;
@@ -614,19 +620,22 @@ static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
 }
 
 struct RenderLayout {
-    int Hc, Wc;
+    int Hc, Wc, Hc2, Wc2;
     bool coarse_enabled, coarse_diffuse_ok;
-    float coarse_h;
+    float coarse_h, coarse2_h;
     bool far_pair;  // the raw-map launch is split into a far launch (16x16-cell blocks) and a near launch
-    RenderPlan raw, far, diff, coarse;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse map
+    RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
     RenderConst* rc;
-    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *slab_raw, *slab_far, *slab_diff, *slab_coarse;
+    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_diff, *slab_coarse, *slab_coarse2;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
     L.Hc = (He + COARSE - 1) / COARSE;
     L.Wc = (We + COARSE - 1) / COARSE;
+    L.Hc2 = (He + COARSE2 - 1) / COARSE2;
+    L.Wc2 = (We + COARSE2 - 1) / COARSE2;
     L.coarse_h = (float)(COARSE * M_PI / He);
+    L.coarse2_h = (float)(COARSE2 * M_PI / He);
     const char* cv = getenv("DRM_RENDER_COARSE");  // "0" disables the coarse-map routes (debugging / validation)
     L.coarse_enabled = !(cv && cv[0] == '0') && He >= 8 * COARSE && We >= 8 * COARSE;
     L.coarse_diffuse_ok = L.coarse_enabled && L.coarse_h <= 0.0135f;
@@ -635,6 +644,7 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE));
     L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2));
     L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S));
+    L.coarse2 = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S));
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -643,10 +653,12 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.sin_p = c.take<float>(We);
     L.cos_p = c.take<float>(We);
     L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
+    L.coarse2_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc2 * L.Wc2 * COARSE_FLOATS : 1);
     L.slab_raw = c.take<float>(slice * L.raw.splits);
     L.slab_far = c.take<float>(L.far_pair ? slice * L.far.splits : 1);
     L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
+    L.slab_coarse2 = c.take<float>(L.coarse_enabled ? slice * L.coarse2.splits : 1);
     return c.used();
 }
 
@@ -766,14 +778,19 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     const int tb = 128;
     render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(L.sin_t, L.cos_t, L.sin_p, L.cos_p, He, We);
     render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale,
-                                                         L.coarse_enabled ? L.coarse_h : 0.f, L.coarse_diffuse_ok ? 1 : 0,
+                                                         L.coarse_enabled ? L.coarse_h : 0.f,
+                                                         L.coarse_enabled ? L.coarse2_h : 0.f, L.coarse_diffuse_ok ? 1 : 0,
                                                          L.rc);
     count_launches(2);
     if (L.coarse_enabled) {
         const long cells = (long)B * L.Hc * L.Wc;
         env_coarsen_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, B, He,
-                                                                            We, L.Hc, L.Wc, g.domega_k, L.coarse_map);
-        count_launches(1);
+                                                                            We, L.Hc, L.Wc, COARSE, g.domega_k, L.coarse_map);
+        const long cells2 = (long)B * L.Hc2 * L.Wc2;
+        env_coarsen_kernel<<<(unsigned)((cells2 + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, B, He,
+                                                                             We, L.Hc2, L.Wc2, COARSE2, g.domega_k,
+                                                                             L.coarse2_map);
+        count_launches(2);
     }
 
     auto fill_plan = [&](GatherArgs& a, const RenderPlan& p) {
@@ -836,6 +853,18 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         fill_plan(a, L.coarse);
         set_levels(a, S, hierarchy);
         if ((rc_code = launch_gather<3, true>(a, tmap, L.coarse, N, st)) != DRM_OK) return rc_code;
+        // the 2x2 coarsening: both lobes of the moderately rough renders
+        GatherArgs a2 = g;
+        a2.src = L.coarse2_map; a2.Hm = L.Hc2; a2.Wm = L.Wc2;
+        a2.dth_cell = (float)(COARSE2 * M_PI / He); a2.dph_cell = (float)(COARSE2 * 2.0 * M_PI / We);
+        CUtensorMap tmap2;
+        memset(&tmap2, 0, sizeof(tmap2));
+        a2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
+        if (a2.use_tma && (rc_code = make_tensor_map(&tmap2, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS)) != DRM_OK) return rc_code;
+        a2.slab = L.slab_coarse2; a2.route_mask = ROUTE_BOTH_COARSE2;
+        fill_plan(a2, L.coarse2);
+        set_levels(a2, S, hierarchy);
+        if ((rc_code = launch_gather<3, true>(a2, tmap2, L.coarse2, N, st)) != DRM_OK) return rc_code;
     }
     {
         SlabDesc s0{L.slab_raw, L.raw.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
@@ -843,7 +872,8 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
         SlabDesc s3{used_far ? L.slab_far : nullptr, L.far.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
         const size_t total = (size_t)N * res * res * 3;
-        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, L.rc, out, N, res, channel_first);
+        SlabDesc s4{L.coarse_enabled ? L.slab_coarse2 : nullptr, L.coarse2.splits, ROUTE_BOTH_COARSE2};
+        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, L.rc, out, N, res, channel_first);
         count_launches(1);
     }
     DRM_CHECK_CUDA(cudaGetLastError());

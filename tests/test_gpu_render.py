@@ -201,7 +201,10 @@ def test_hierarchy_parity_vs_oracle_windows(zname):
 
 
 # ---- coarse-map routes (diffuse lobe / very rough specular lobe gathered from the 4x4 energy-centroid map) ----------
-@pytest.mark.parametrize("zname,S", [("rough_dielectric", 1), ("mixed", 2), ("random7", 2)])
+Z_CASES["moderately_rough"] = [0.5, 0.9, 0.8, 0.3, 0.62, 0.7]
+
+
+@pytest.mark.parametrize("zname,S", [("rough_dielectric", 1), ("mixed", 2), ("random7", 2), ("moderately_rough", 1)])
 def test_coarse_routes_match_raw_map_full_size(zname, S):
     """2000x1000 -> 128x128, all pixels: routes through the coarse map against everything gathered from the raw map."""
     env = synthetic_envmap(1000, 2000, seed=1004, device=DEV)[None]
@@ -213,9 +216,11 @@ def test_coarse_routes_match_raw_map_full_size(zname, S):
     assert rel_l2(fast.cpu().numpy(), full.cpu().numpy()) <= 7e-5
 
 
-@pytest.mark.parametrize("z", [[0.2, 0.9, 0.8, 0.7, 0.85, 0.6], [0.0, 1.0, 1.0, 1.0, 0.3, 0.0], [1.0, 0.9, 0.5, 0.3, 1.0, 1.0]])
+@pytest.mark.parametrize("z", [[0.2, 0.9, 0.8, 0.7, 0.85, 0.6], [0.0, 1.0, 1.0, 1.0, 0.3, 0.0], [1.0, 0.9, 0.5, 0.3, 1.0, 1.0],
+                               [0.5, 0.9, 0.8, 0.3, 0.62, 0.7], [1.0, 1.0, 0.9, 0.8, 0.6, 1.0]])
 def test_coarse_routes_parity_vs_oracle_full_size(z):
-    """Very rough (both lobes from the coarse map), diffuse-dominated (diffuse from the coarse map), rough metal."""
+    """Very rough (both lobes from the 4x4 map), diffuse-dominated (diffuse from the 4x4 map), rough metal, and two
+    moderately rough cases (both lobes from the 2x2 map)."""
     env = synthetic_envmap(1000, 2000, seed=1007)
     ours = _render(env[None], [z], [VIEWS[3]], 16, 1, channel_first=False)[0]
     assert rel_l2(ours, render_oracle(env, z, VIEWS[3], 16, S=1)) <= TOL
