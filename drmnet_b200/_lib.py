@@ -53,6 +53,10 @@ def lib() -> ctypes.CDLL:
     L.drm_refmap_postprocess.argtypes = [vp, i32, i32, i32, f32, i32, vp, vp, vp]
     L.drm_mirmap2envmap.restype = i32
     L.drm_mirmap2envmap.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.drm_refmap_lookup.restype = i32
+    L.drm_refmap_lookup.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
+    L.drm_normalized_log.restype = i32
+    L.drm_normalized_log.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]
     L.drm_normals_to_thetaphi.restype = i32
     L.drm_normals_to_thetaphi.argtypes = [vp, i64, vp, vp]
     _lib = L
@@ -69,4 +73,4 @@ def check(code: int) -> None:
 
 EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_launch_count", "drm_render_workspace_bytes", "drm_render_refmaps",
                     "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_normals_to_thetaphi",
-                    "drm_refmap_postprocess", "drm_mirmap2envmap"]
+                    "drm_refmap_postprocess", "drm_mirmap2envmap", "drm_refmap_lookup", "drm_normalized_log"]

@@ -125,3 +125,45 @@ def r0toenvmap(r0: torch.Tensor, basis_r0: torch.Tensor, envshape: Optional[Tupl
     if envshape is None:
         envshape = (r0.shape[-2], r0.shape[-1] * 2)
     return mirmap2envmap(r0, envshape, basis=basis_r0).permute(0, 2, 3, 1)
+
+
+def refmap_lookup(refmap: torch.Tensor, normals: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Shade pixels by their normals: colors [n,C] = bilinear lookup of refmap [B,C,H,W] (or [C,H,W]) at the (theta, phi)
+    of normals [n,3]; image b owns rows offsets[b]:offsets[b+1].  The arithmetic of refmap2refimg_torch
+    (utils/transform.py:170-198) for arbitrary object normals -- the stand-in for the reference's mesh path tracer in
+    the parametric_img2refmap flow."""
+    if not refmap.is_cuda:
+        raise RuntimeError("refmap must be a CUDA tensor: drmnet_b200 has no CPU path")
+    if refmap.dim() == 3:
+        refmap = refmap[None]
+    refmap = refmap.contiguous().float()
+    normals = normals.to(refmap.device).contiguous().float()
+    B, C, H, W = refmap.shape
+    n = normals.shape[0]
+    if offsets is None:
+        assert B == 1
+        offsets = torch.tensor([0, n], dtype=torch.int64, device=refmap.device)
+    offsets = offsets.to(device=refmap.device, dtype=torch.int64).contiguous()
+    colors = torch.empty((n, C), dtype=torch.float32, device=refmap.device)
+    with torch.cuda.device(refmap.device):
+        _lib.check(_lib.lib().drm_refmap_lookup(refmap.data_ptr(), normals.data_ptr(), offsets.data_ptr(), n, B, C, H, W,
+                                                colors.data_ptr(), _stream(refmap.device)))
+    return colors
+
+
+def normalized_log_transform(x: torch.Tensor, mask: torch.Tensor, lowerbound: float = 1e-6):
+    """ObsNet's conditioning transform `0p1tom1p1_normalizedLogarithmic_lowerbound1e-6` with dynamic_normalize=True
+    (dataset/basedataset.py:56-76; models/obsnet.py:224,370): x [B,C,H,W], mask [B,1,H,W] or [B,H,W].
+    Returns (out [B,C,H,W] in [-1,1] over the mask, (log10min [B], log10max [B]))."""
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor: drmnet_b200 has no CPU path")
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    mask = mask.to(x.device).float().reshape(B, H, W).contiguous()
+    out = torch.empty_like(x)
+    lmin = torch.empty(B, dtype=torch.float32, device=x.device)
+    lmax = torch.empty(B, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().drm_normalized_log(x.data_ptr(), mask.data_ptr(), B, C, H, W, float(lowerbound),
+                                                 out.data_ptr(), lmin.data_ptr(), lmax.data_ptr(), _stream(x.device)))
+    return out, (lmin, lmax)

@@ -99,9 +99,103 @@ __global__ void mirmap2envmap_kernel(const float* __restrict__ mir, const float*
         }
 }
 
+// N3: shade pixels by a bilinear refmap lookup at the (theta, phi) of their normals -- the arithmetic of
+// refmap2refimg_torch (utils/transform.py:170-198: xyz2thetaphi(normal,[0,1,0],[-1,0,0]) -> uv = (phi, theta) * 2/pi - 1
+// -> grid_sample bilinear / border / align_corners=False), for arbitrary normal lists (object images), batched by offsets.
+__global__ void refmap_lookup_kernel(const float* __restrict__ refmap, const float* __restrict__ normals,
+                                     const int64_t* __restrict__ offsets, int64_t total_n, int B, int C, int H, int W,
+                                     float* __restrict__ colors) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= total_n) return;
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= p) lo = mid; else hi = mid;
+    }
+    const float x = normals[3 * p], y = normals[3 * p + 1], z = normals[3 * p + 2];
+    const float th = acosf(y), ph = atan2f(z, -x + 0.f);
+    const float u = ph * (float)(2.0 / M_PI) - 1.f, v = th * (float)(2.0 / M_PI) - 1.f;
+    float ix = ((u + 1.f) * W - 1.f) * 0.5f, iy = ((v + 1.f) * H - 1.f) * 0.5f;
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    for (int c = 0; c < C; ++c) {
+        const float* m = refmap + ((size_t)lo * C + c) * H * W;
+        colors[p * C + c] = m[y0 * W + x0] * (wx0 * wy0) + m[y0 * W + x1] * (wx1 * wy0) + m[y1 * W + x0] * (wx0 * wy1) +
+                            m[y1 * W + x1] * (wx1 * wy1);
+    }
+}
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float t = sh[0];
+    for (int i = 1; i < POST_THREADS / 32; ++i) t = fmaxf(t, sh[i]);
+    __syncthreads();
+    return t;
+}
+
+// N4: ObsNet's conditioning transform chain `0p1tom1p1_normalizedLogarithmic_lowerbound<lb>` with dynamic_normalize
+// (dataset/basedataset.py:56-76 applied right to left; models/obsnet.py:224,370): y = clip(x, lb);
+// max = amax(y * mask), min = amin(y * mask + (1 - mask) * max) per sample; out = 2 (log10 y - log10 min)/(log10 max - log10 min) - 1.
+__global__ void __launch_bounds__(POST_THREADS) normalized_log_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ mask, int C, int P,
+                                                                      float lowerbound, float* __restrict__ out,
+                                                                      float* __restrict__ log10min_out,
+                                                                      float* __restrict__ log10max_out) {
+    __shared__ float sh[POST_THREADS / 32];
+    const int n = blockIdx.x;
+    const float* xs = x + (size_t)n * C * P;
+    const float* ms = mask + (size_t)n * P;
+    float mx = -INFINITY;
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS) mx = fmaxf(mx, fmaxf(xs[e], lowerbound) * ms[e % P]);
+    mx = block_max(mx, sh);
+    float mn = -INFINITY;  // max of the negated values = -min
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS) {
+        const float m = ms[e % P];
+        mn = fmaxf(mn, -(fmaxf(xs[e], lowerbound) * m + (1.f - m) * mx));
+    }
+    mn = -block_max(mn, sh);
+    const float lmax = log10f(mx), lmin = log10f(mn);
+    if (threadIdx.x == 0) {
+        if (log10min_out) log10min_out[n] = lmin;
+        if (log10max_out) log10max_out[n] = lmax;
+    }
+    const float inv = 1.f / (lmax - lmin);
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS)
+        out[(size_t)n * C * P + e] = (log10f(fmaxf(xs[e], lowerbound)) - lmin) * inv * 2.f - 1.f;
+}
+
 }  // namespace drm
 
 using namespace drm;
+
+extern "C" int drm_refmap_lookup(const float* refmap, const float* normals, const int64_t* offsets, int64_t total_n,
+                                 int B, int C, int H, int W, float* colors, void* cuda_stream) {
+    DRM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && total_n >= 0, "refmap_lookup: sizes must be positive");
+    DRM_REQUIRE(refmap && offsets && (total_n == 0 || (normals && colors)), "refmap_lookup: null pointer");
+    if (total_n == 0) return DRM_OK;
+    refmap_lookup_kernel<<<(unsigned)((total_n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        refmap, normals, offsets, total_n, B, C, H, W, colors);
+    DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DRM_OK;
+}
+
+extern "C" int drm_normalized_log(const float* x, const float* mask, int B, int C, int H, int W, float lowerbound,
+                                  float* out, float* log10min_out, float* log10max_out, void* cuda_stream) {
+    DRM_REQUIRE(x && mask && out, "normalized_log: null pointer");
+    DRM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "normalized_log: sizes must be positive");
+    normalized_log_kernel<<<B, POST_THREADS, 0, static_cast<cudaStream_t>(cuda_stream)>>>(x, mask, C, H * W, lowerbound, out,
+                                                                                         log10min_out, log10max_out);
+    DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DRM_OK;
+}
 
 extern "C" int drm_refmap_postprocess(const float* in, int G, int N, int res, float target, int transform,
                                       float* scale_out, float* out, void* cuda_stream) {

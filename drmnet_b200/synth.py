@@ -117,3 +117,18 @@ def sphere_image_inputs(radius: int, seed: int, noise: float = 0.05):
         + 40.0 * np.exp(-((nrm[:, :1] - 0.3) ** 2 + (nrm[:, 1:2] - 0.5) ** 2) / 0.002)
     col = col * (1 + 0.01 * rng.normal(size=col.shape))
     return col.astype(np.float32), nrm.astype(np.float32)
+
+
+def sphere_normals(radius):
+    """gen_sphere_normals_realcentering (utils/transform.py:147-167) restated: x right, y up, z toward the viewer."""
+    ax = np.linspace(-radius + 0.5, radius - 0.5, 2 * radius)
+    x, y = np.meshgrid(ax, -ax)
+    zsq = radius ** 2 - (x ** 2 + y ** 2)
+    n = np.zeros((2 * radius, 2 * radius, 3), np.float32)
+    n[..., 0], n[..., 1] = x, y
+    n[zsq >= 0, 2] = np.sqrt(zsq[zsq >= 0])
+    n /= np.sqrt((n ** 2).sum(-1, keepdims=True))
+    n[zsq < 0] = 0
+    ii, jj = np.ogrid[0:2 * radius, 0:2 * radius]
+    mask = ((ii + 0.5 - radius) ** 2 + (jj + 0.5 - radius) ** 2) <= radius * radius
+    return n * mask[..., None], mask

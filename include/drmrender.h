@@ -98,6 +98,17 @@ int drm_refmap_postprocess(const float* in, int G, int N, int res, float target,
 int drm_mirmap2envmap(const float* mirmap, const float* basis, int B, int C, int H, int W, int OH, int OW,
                       float* out, void* cuda_stream);
 
+/* N3: colors[p, :] = bilinear lookup of refmap[b] (refmap [B, C, H, W]) at the (theta, phi) of normals[p] for the pixels
+ * p of image b (offsets [B+1] int64) -- refmap2refimg_torch (utils/transform.py:170-198) for arbitrary normal lists. */
+int drm_refmap_lookup(const float* refmap, const float* normals, const int64_t* offsets, int64_t total_n,
+                      int B, int C, int H, int W, float* colors, void* cuda_stream);
+
+/* N4: ObsNet conditioning transform `0p1tom1p1_normalizedLogarithmic_lowerbound<lb>` with dynamic normalisation under a
+ * mask (dataset/basedataset.py:56-76, models/obsnet.py:224,370): x [B, C, H, W], mask [B, H, W] float 0/1;
+ * log10min_out / log10max_out [B] receive the per-sample parameters (may be NULL). */
+int drm_normalized_log(const float* x, const float* mask, int B, int C, int H, int W, float lowerbound,
+                       float* out, float* log10min_out, float* log10max_out, void* cuda_stream);
+
 /* angles only: [n,3] normals -> [n,2] (theta, phi), the arithmetic of utils/transform.py:84-89 at img2refmap.py:20 */
 int drm_normals_to_thetaphi(const float* normals, int64_t n, float* thetaphi, void* cuda_stream);
 

@@ -48,3 +48,33 @@ def mirmap2envmap_oracle(mirmap, output_shape, basis=None):
     out = (m[:, :, y0, x0] * (1 - wx) * (1 - wy) + m[:, :, y0, x1] * wx * (1 - wy)
            + m[:, :, y1, x0] * (1 - wx) * wy + m[:, :, y1, x1] * wx * wy)
     return out
+
+
+def refmap_lookup_oracle(refmap, normals):
+    """refmap [C,H,W], normals [n,3] -> [n,C]: utils/transform.py:170-198 (uv from xyz2thetaphi(n,[0,1,0],[-1,0,0]),
+    grid_sample bilinear / border / align_corners=False), float64."""
+    m = np.asarray(refmap, dtype=np.float64)
+    n = np.asarray(normals, dtype=np.float64)
+    C, H, W = m.shape
+    th = np.arccos(np.clip(n[:, 1], -1, 1))
+    ph = np.arctan2(n[:, 2], -n[:, 0] + 0.0)
+    u, v = ph * (2 / np.pi) - 1, th * (2 / np.pi) - 1
+    ix = np.clip(((u + 1) * W - 1) / 2, 0, W - 1)
+    iy = np.clip(((v + 1) * H - 1) / 2, 0, H - 1)
+    x0, y0 = np.floor(ix).astype(int), np.floor(iy).astype(int)
+    wx, wy = ix - x0, iy - y0
+    x1, y1 = np.minimum(x0 + 1, W - 1), np.minimum(y0 + 1, H - 1)
+    out = (m[:, y0, x0] * (1 - wx) * (1 - wy) + m[:, y0, x1] * wx * (1 - wy)
+           + m[:, y1, x0] * (1 - wx) * wy + m[:, y1, x1] * wx * wy)
+    return out.T
+
+
+def normalized_log_oracle(x, mask, lowerbound=1e-6):
+    """dataset/basedataset.py:56-76 for `0p1tom1p1_normalizedLogarithmic_lowerbound<lb>` with dynamic_normalize."""
+    x = np.clip(np.asarray(x, dtype=np.float64), lowerbound, None)
+    m = np.asarray(mask, dtype=np.float64).reshape(x.shape[0], 1, x.shape[2], x.shape[3])
+    linearmax = (x * m).max(axis=(1, 2, 3), keepdims=True)
+    log10max = np.log10(linearmax)
+    log10min = np.log10((x * m + (1 - m) * linearmax).min(axis=(1, 2, 3), keepdims=True))
+    y = (np.log10(x) - log10min) / (log10max - log10min)
+    return y * 2 - 1, log10min.reshape(-1), log10max.reshape(-1)

@@ -8,7 +8,8 @@ What is produced
                           and refmap_mask_make (utils/img2refmap.py:6-37) -- BASELINE config[0].
 * img2refmap_synth.npz    seeded synthetic cases covering thresholds != half a cell (multi-membership
                           and dropped pixels), min_points, NaN colours, exact ties, non-unit normals.
-* mirmap_ref.npz          the reference's only torch renderer, envmap2mirmap (utils/transform.py:201-242),
+* mirmap_ref.npz          (also: refmap2refimg_torch on a random refmap, utils/transform.py:170-198)
+                          the reference's only torch renderer, envmap2mirmap (utils/transform.py:201-242),
                           on a seeded synthetic envmap: the mirror-limit known answer, plus
                           mirmap2envmap (utils/transform.py:106-144) for the round trip (K3).
 """
@@ -29,7 +30,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from utils.img2refmap import refmap_mask_make  # noqa: E402  (the reference)
-from utils.transform import envmap2mirmap, mirmap2envmap, xyz2thetaphi  # noqa: E402
+from utils.transform import envmap2mirmap, mirmap2envmap, refmap2refimg_torch, xyz2thetaphi  # noqa: E402
 
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -140,6 +141,13 @@ def main():
         blob[f"view_{tag}"] = np.asarray(view, np.float32)
     mir = torch.from_numpy(blob["mirmap_v001"]).permute(2, 0, 1)[None]
     blob["envmap_from_mirmap_v001"] = mirmap2envmap(mir, (32, 64))[0].permute(1, 2, 0).numpy()
+    # sphere image shaded by a refmap lookup: the reference's refmap2refimg_torch (utils/transform.py:170-198)
+    g = torch.Generator().manual_seed(3)
+    refmap = torch.exp(torch.randn(1, 3, 32, 32, generator=g))
+    img, msk = refmap2refimg_torch(refmap, radius=24, return_mask=True)
+    blob["refimg_refmap"] = refmap[0].numpy()
+    blob["refimg_image"] = img[0].numpy()
+    blob["refimg_mask"] = msk.numpy()
     np.savez_compressed(OUT / "mirmap_ref.npz", **blob)
     print("wrote", sorted(p.name for p in OUT.glob("*.npz")))
 

@@ -69,3 +69,64 @@ def test_batched_callers_equal_the_reference_loop():
     assert np.allclose(scale.cpu().numpy(), s, rtol=1e-5)
     for gi in range(4):
         assert np.abs(outs[gi].cpu().numpy() - ref[gi]).max() < 1e-4
+
+
+def test_refmap_lookup_matches_reference_and_oracle(golden_mirmap):
+    from drmnet_b200.callers import refmap_lookup
+    from oracle.callers_oracle import refmap_lookup_oracle
+    from drmnet_b200.synth import sphere_normals
+    n, mask = sphere_normals(24)
+    refmap = torch.from_numpy(golden_mirmap["refimg_refmap"]).to(DEV)
+    ours = refmap_lookup(refmap, torch.from_numpy(n[mask]).to(DEV)).cpu().numpy()
+    ref = golden_mirmap["refimg_image"][:, mask].T  # the reference's refmap2refimg_torch
+    assert np.abs(ours - ref).max() <= 3e-5 * np.abs(ref).max()
+    # batched, arbitrary normals
+    g = torch.Generator().manual_seed(5)
+    maps = torch.exp(torch.randn(3, 3, 64, 64, generator=g)).to(DEV)
+    nrm = torch.nn.functional.normalize(torch.randn(5000, 3, generator=g), dim=-1)
+    offsets = torch.tensor([0, 1000, 1000, 5000])
+    out = refmap_lookup(maps, nrm, offsets).cpu().numpy()
+    for b, (lo, hi) in enumerate([(0, 1000), (1000, 1000), (1000, 5000)]):
+        if hi > lo:
+            o = refmap_lookup_oracle(maps[b].cpu().numpy(), nrm[lo:hi].numpy())
+            assert np.abs(out[lo:hi] - o).max() <= 3e-5 * np.abs(o).max()
+
+
+def test_normalized_log_transform_matches_oracle():
+    from drmnet_b200.callers import normalized_log_transform
+    from oracle.callers_oracle import normalized_log_oracle
+    g = torch.Generator().manual_seed(6)
+    x = torch.exp(torch.randn(4, 3, 128, 128, generator=g) * 2)
+    x[1, :, :5] = 0.0
+    mask = (torch.rand(4, 1, 128, 128, generator=g) > 0.4)
+    out, (lmin, lmax) = normalized_log_transform(x.to(DEV), mask.to(DEV))
+    ref, rmin, rmax = normalized_log_oracle(x.numpy(), mask.numpy())
+    assert np.allclose(lmin.cpu().numpy(), rmin, atol=2e-6) and np.allclose(lmax.cpu().numpy(), rmax, atol=2e-6)
+    assert np.abs(out.cpu().numpy() - ref).max() < 2e-5
+
+
+def test_config3_pipeline_render_shade_scatter_round_trip():
+    """BASELINE config[2] data flow (parametricrefmap + parametric_img2refmap): render a refmap, shade a 256^2 sphere image
+    with it (N3 stand-in for the mesh renderer), scatter the image back into a refmap (K2).  Every filled cell must hold a
+    bilinear sample of the rendered refmap taken inside that cell: within the cell's neighbourhood range."""
+    from drmnet_b200.callers import refmap_lookup
+    from drmnet_b200.img2refmap import img2refmap_batch
+    from drmnet_b200.renderer import render_batch
+    from drmnet_b200.synth import sphere_normals
+    res = 128
+    env = torch.from_numpy(synthetic_envmap(250, 500, seed=9)).to(DEV)
+    z = torch.tensor([[0.3, 0.8, 0.6, 0.4, 0.5, 0.7]])
+    refmap = render_batch(env[None], z, torch.tensor([[0.0, 0.0, 1.0]]), res=res, footprint_S=1)  # [1,3,res,res]
+    n, mask = sphere_normals(128)
+    normals = torch.from_numpy(n[mask]).to(DEV)
+    colors = refmap_lookup(refmap, normals)
+    offsets = torch.tensor([0, normals.shape[0]], dtype=torch.int64, device=DEV)
+    back, filled, counts, _ = img2refmap_batch(colors, normals, offsets, res, float(np.pi / res / 2))
+    back, filled, src = back[0].cpu().numpy(), filled[0].cpu().numpy(), refmap[0].permute(1, 2, 0).cpu().numpy()
+    assert filled.sum() > 0.6 * res * res
+    pad = np.pad(src, ((1, 1), (1, 1), (0, 0)), mode="edge")
+    lo = np.minimum.reduce([pad[1 + di:res + 1 + di, 1 + dj:res + 1 + dj] for di in (-1, 0, 1) for dj in (-1, 0, 1)])
+    hi = np.maximum.reduce([pad[1 + di:res + 1 + di, 1 + dj:res + 1 + dj] for di in (-1, 0, 1) for dj in (-1, 0, 1)])
+    ok = (back >= lo * (1 - 1e-5)) & (back <= hi * (1 + 1e-5))
+    assert ok[filled].all()
+    assert rel_l2(back[filled], src[filled]) < 0.05

@@ -2,6 +2,7 @@
 import numpy as np
 import torch
 
+from drmnet_b200.synth import sphere_normals
 from oracle.callers_oracle import mirmap2envmap_oracle, postprocess_oracle
 
 
@@ -27,3 +28,30 @@ def test_postprocess_oracle_matches_torch_formulas():
     ours, s = postprocess_oracle(stacks.numpy())
     assert np.allclose(s, scale.numpy(), rtol=1e-5)
     assert np.allclose(ours, ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_refmap_lookup_oracle_matches_reference_refmap2refimg(golden_mirmap):
+    """golden: the reference's refmap2refimg_torch (utils/transform.py:170-198) on a random 32x32 refmap, radius 24."""
+    from oracle.callers_oracle import refmap_lookup_oracle
+    n, mask = sphere_normals(24)
+    assert np.array_equal(mask, golden_mirmap["refimg_mask"])
+    ours = refmap_lookup_oracle(golden_mirmap["refimg_refmap"], n[mask])
+    ref = golden_mirmap["refimg_image"][:, mask].T
+    assert np.abs(ours - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+def test_normalized_log_oracle_matches_torch_formulas():
+    """dataset/basedataset.py:56-76 evaluated with torch ops, chain lowerbound1e-6 -> normalizedLogarithmic -> 0p1tom1p1."""
+    from oracle.callers_oracle import normalized_log_oracle
+    g = torch.Generator().manual_seed(2)
+    x = torch.exp(torch.randn(3, 3, 16, 16, generator=g) * 2)
+    x[0, 0, 0, 0] = 0.0
+    mask = (torch.rand(3, 1, 16, 16, generator=g) > 0.3).float()
+    y = torch.clip(x, 1e-6)
+    linearmax = (y * mask).amax(dim=(-1, -2, -3), keepdim=True)
+    log10max = torch.log10(linearmax)
+    log10min = torch.log10((y * mask + (1 - mask) * linearmax).amin(dim=(-1, -2, -3), keepdim=True))
+    ref = (torch.log10(y) - log10min) / (log10max - log10min) * 2 - 1
+    ours, lmin, lmax = normalized_log_oracle(x.numpy(), mask.numpy())
+    assert np.allclose(ours, ref.numpy(), rtol=1e-5, atol=1e-5)
+    assert np.allclose(lmin, log10min.reshape(-1).numpy(), atol=1e-6) and np.allclose(lmax, log10max.reshape(-1).numpy(), atol=1e-6)
