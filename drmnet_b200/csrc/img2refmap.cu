@@ -7,8 +7,9 @@
 // under the total order (channel-sum, pixel index).  Integer atomics only place pairs inside a cell's segment; the
 // selection is order-independent, so every output is bit-exact and run-to-run deterministic.
 //
-// HBM-bound integer/compare work: no tensor cores.  Traffic per image: normals+colours read by the two pixel
-// passes (second pass is an L2 hit for batches that fit), 8 B per pair written and read once, 4 int32 per cell.
+// HBM-bound integer/compare work: no tensor cores.  Traffic per image: normals and colours are read once (the first
+// pass leaves each pixel's cell id for the second), 8 B per pair written and read once, 4 int32 per cell.  Atomics are
+// aggregated per warp (__match_any_sync): raster-ordered pixels of an image mostly share their neighbours' cell.
 #include <math.h>
 
 #include "common.cuh"
@@ -16,6 +17,8 @@
 namespace drm {
 
 static constexpr uint32_t KEY_NAN = 0xFFFFFFFFu;  // sentinel: colour sum is NaN (ignored by nanmedian, :30-31)
+static constexpr uint32_t CELL_NONE = 0x7FFFFFFFu, CELL_MULTI = 0x80000000u;
+static constexpr int SMALL_MAX = 48;  // cells up to this size are selected by one thread
 
 struct I2RArgs {
     const float* colors;
@@ -35,7 +38,10 @@ struct I2RArgs {
     int32_t* nan_count;   // [B]
     int32_t* nan_list;    // [total_n]  (image b owns the slice starting at offsets[b])
     int32_t* block_sums;  // scan scratch
-    uint2* pairs;         // (key, image-local pixel index)
+    uint2* pairs;         // (key, global pixel index)
+    uint32_t* cell0;      // [total_n] first cell of each pixel (CELL_NONE if none), bit 31 set if it has more cells
+    int32_t* big_list;    // [M] cells left to the warp-per-cell select (large, NaN-angle members, mean mode)
+    int32_t* big_count;   // [1]
     int32_t* status;      // bit 0: pair buffer overflow
     // outputs
     float* refmap;
@@ -72,6 +78,16 @@ __device__ __forceinline__ int image_of(const int64_t* __restrict__ offsets, int
     return lo;
 }
 
+// image of pixel p: one binary search per CTA (for its first pixel, by thread 0), then a short forward walk per thread
+__device__ __forceinline__ int image_of_cta(const int64_t* __restrict__ offsets, int B, int64_t p, int64_t cta_first) {
+    __shared__ int b0;
+    if (threadIdx.x == 0) b0 = image_of(offsets, B, cta_first);
+    __syncthreads();
+    int b = b0;
+    while (b + 1 < B && offsets[b + 1] <= p) ++b;
+    return b;
+}
+
 // monotone uint key of the fp32 channel sum; -0.0 and +0.0 share a key (torch compares them equal)
 __device__ __forceinline__ uint32_t sum_key(const float* __restrict__ c, int C) {
     float s = c[0];
@@ -82,14 +98,31 @@ __device__ __forceinline__ uint32_t sum_key(const float* __restrict__ c, int C) 
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// PASS = 0: histogram; PASS = 1: scatter pairs into the cell segments
-template <int PASS>
-__global__ void __launch_bounds__(256) i2r_pixel_pass(I2RArgs a) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= a.total_n) return;
-    const int b = image_of(a.offsets, a.B, p);
+// One warp-wide increment per distinct cell: lanes that target the same cell elect a leader (raster-ordered pixels
+// mostly share their neighbours' cell).  Returns the lane's rank inside its group and the group's base (PASS 1).
+__device__ __forceinline__ int warp_claim(int32_t* counter, bool valid, int64_t gbin, bool want_base, int& rank) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long key = valid ? (unsigned long long)gbin : (0x8000000000000000ull | lane);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    rank = __popc(grp & ((1u << lane) - 1u));
+    int base = 0;
+    if (valid && (int)lane == leader) {
+        if (want_base) base = atomicAdd(&counter[gbin], __popc(grp));
+        else atomicAdd(&counter[gbin], __popc(grp));
+    }
+    if (want_base) base = __shfl_sync(0xffffffffu, base, leader);
+    return base;
+}
+
+// PASS 0: angles, window predicate, histogram of the cells, first cell of each pixel left in cell0
+__global__ void __launch_bounds__(256) i2r_hist_pass(I2RArgs a) {
+    const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t p = cta_first + threadIdx.x;
+    const bool in_range = p < a.total_n;
+    const int b = image_of_cta(a.offsets, a.B, in_range ? p : a.total_n - 1, cta_first);
+    if (!in_range) return;
     const int64_t base = a.offsets[b];
-    const int local = (int)(p - base);
     float th, ph;
     if (a.is_thetaphi) {
         th = a.geom[2 * p];
@@ -99,33 +132,78 @@ __global__ void __launch_bounds__(256) i2r_pixel_pass(I2RArgs a) {
     }
     if (isnan(th) || isnan(ph)) {
         // 'NaN > thr' is False (img2refmap.py:27): the pixel is a member of every cell of its image
-        if (PASS == 0) {
-            int slot = atomicAdd(&a.nan_count[b], 1);
-            a.nan_list[base + slot] = local;
-        }
+        const int slot = atomicAdd(&a.nan_count[b], 1);
+        a.nan_list[base + slot] = (int32_t)(p - base);
+        a.cell0[p] = CELL_NONE;
         return;
     }
-    uint32_t key = 0;
-    if (PASS == 1) key = sum_key(a.colors + p * a.C, a.C);
-    // candidate cells: floor bin +- R; the fp32 predicate below alone decides membership
-    const float fi = floorf(th * a.inv_step), fj = floorf(ph * a.inv_step);
+    bool have = false, multi = false;
+    int64_t first = 0;
+    // candidate cells: those whose centre can lie within thr of the angle, +-1 for rounding; the fp32 predicate below
+    // alone decides membership
     const float lim = (float)a.res + (float)a.R + 1.f;
-    if (!(fi > -lim && fi < lim && fj > -lim && fj < lim)) return;  // also rejects +-inf
-    const int i0 = (int)fi, j0 = (int)fj;
-    const int ilo = max(i0 - a.R, 0), ihi = min(i0 + a.R, a.res - 1);
-    const int jlo = max(j0 - a.R, 0), jhi = min(j0 + a.R, a.res - 1);
-    for (int i = ilo; i <= ihi; ++i) {
-        const float ci = __fmul_rn((float)i + 0.5f, a.stepf);  // (arange + 0.5) * (pi / res), img2refmap.py:16
-        if (fabsf(__fsub_rn(ci, th)) > a.thr) continue;
-        for (int j = jlo; j <= jhi; ++j) {
-            const float cj = __fmul_rn((float)j + 0.5f, a.stepf);
-            if (fabsf(__fsub_rn(cj, ph)) > a.thr) continue;
-            const int64_t gbin = (int64_t)b * a.res2 + (int64_t)i * a.res + j;
-            if (PASS == 0) {
+    const float flo_i = floorf((th - a.thr) * a.inv_step - 0.5f), fhi_i = floorf((th + a.thr) * a.inv_step - 0.5f);
+    const float flo_j = floorf((ph - a.thr) * a.inv_step - 0.5f), fhi_j = floorf((ph + a.thr) * a.inv_step - 0.5f);
+    if (fhi_i > -lim && flo_i < lim && fhi_j > -lim && flo_j < lim) {  // also rejects +-inf
+        const int ilo = max((int)fmaxf(flo_i, -lim), 0), ihi = min((int)fminf(fhi_i, lim) + 1, a.res - 1);
+        const int jlo = max((int)fmaxf(flo_j, -lim), 0), jhi = min((int)fminf(fhi_j, lim) + 1, a.res - 1);
+        for (int i = ilo; i <= ihi; ++i) {
+            const float ci = __fmul_rn((float)i + 0.5f, a.stepf);  // (arange + 0.5) * (pi / res), img2refmap.py:16
+            if (fabsf(__fsub_rn(ci, th)) > a.thr) continue;
+            for (int j = jlo; j <= jhi; ++j) {
+                const float cj = __fmul_rn((float)j + 0.5f, a.stepf);
+                if (fabsf(__fsub_rn(cj, ph)) > a.thr) continue;
+                const int64_t gbin = (int64_t)b * a.res2 + (int64_t)i * a.res + j;
+                if (!have) { have = true; first = gbin; }
+                else multi = true;
                 atomicAdd(&a.bin_count[gbin], 1);
-            } else {
+            }
+        }
+    }
+    a.cell0[p] = have ? ((uint32_t)first | (multi ? CELL_MULTI : 0u)) : CELL_NONE;
+}
+
+// PASS 1: scatter (sum key, pixel) pairs into the cell segments
+__global__ void __launch_bounds__(256) i2r_scatter_pass(I2RArgs a) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool in_range = p < a.total_n;
+    const uint32_t c0 = in_range ? a.cell0[p] : CELL_NONE;
+    const bool have = c0 != CELL_NONE;
+    const int64_t first = (int64_t)(c0 & ~CELL_MULTI);
+    uint32_t key = 0;
+    if (have) key = sum_key(a.colors + p * a.C, a.C);
+    int rank;
+    const int base = warp_claim(a.cursor, have, first, true, rank);
+    if (have) {
+        const int64_t slot = (int64_t)a.bin_offset[first] + base + rank;
+        if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(key, (uint32_t)p);
+        else atomicOr(a.status, 1);
+    }
+    if (have && (c0 & CELL_MULTI)) {
+        // the pixel's other cells: recompute the window (same arithmetic as the histogram pass), skip the first one
+        const int b = image_of(a.offsets, a.B, p);
+        float th, ph;
+        if (a.is_thetaphi) {
+            th = a.geom[2 * p];
+            ph = a.geom[2 * p + 1];
+        } else {
+            normal_to_thetaphi(a.geom[3 * p], a.geom[3 * p + 1], a.geom[3 * p + 2], th, ph);
+        }
+        const float lim = (float)a.res + (float)a.R + 1.f;
+        const float flo_i = floorf((th - a.thr) * a.inv_step - 0.5f), fhi_i = floorf((th + a.thr) * a.inv_step - 0.5f);
+        const float flo_j = floorf((ph - a.thr) * a.inv_step - 0.5f), fhi_j = floorf((ph + a.thr) * a.inv_step - 0.5f);
+        const int ilo = max((int)fmaxf(flo_i, -lim), 0), ihi = min((int)fminf(fhi_i, lim) + 1, a.res - 1);
+        const int jlo = max((int)fmaxf(flo_j, -lim), 0), jhi = min((int)fminf(fhi_j, lim) + 1, a.res - 1);
+        for (int i = ilo; i <= ihi; ++i) {
+            const float ci = __fmul_rn((float)i + 0.5f, a.stepf);
+            if (fabsf(__fsub_rn(ci, th)) > a.thr) continue;
+            for (int j = jlo; j <= jhi; ++j) {
+                const float cj = __fmul_rn((float)j + 0.5f, a.stepf);
+                if (fabsf(__fsub_rn(cj, ph)) > a.thr) continue;
+                const int64_t gbin = (int64_t)b * a.res2 + (int64_t)i * a.res + j;
+                if (gbin == first) continue;
                 const int64_t slot = (int64_t)a.bin_offset[gbin] + atomicAdd(&a.cursor[gbin], 1);
-                if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(key, (uint32_t)local);
+                if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(key, (uint32_t)p);
                 else atomicOr(a.status, 1);
             }
         }
@@ -200,29 +278,108 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add(int32_t* __restrict__ o
         if (start + k < M) out[start + k] += add;
 }
 
-// ---- one warp per cell: lower median under the total order (sum key, pixel index) ---------------------------
+// ---- selection of the lower median under the total order (sum key, pixel index) ----------------------------------
 struct CellView {
     const uint2* seg;
     int nreg;
-    const int32_t* nan_list;
+    const int32_t* nan_list;  // image-local indices
     int nnan;
-    const float* colors;  // image base
+    int64_t base;             // first pixel of the image
+    const float* colors;      // global
     int C;
-    __device__ __forceinline__ uint64_t get(int e) const {  // (key << 32) | idx
+    __device__ __forceinline__ uint64_t get(int e) const {  // (key << 32) | global pixel index
         if (e < nreg) {
             uint2 pr = seg[e];
             return ((uint64_t)pr.x << 32) | pr.y;
         }
-        int idx = nan_list[e - nreg];
-        return ((uint64_t)sum_key(colors + (int64_t)idx * C, C) << 32) | (uint32_t)idx;
+        const int64_t idx = base + nan_list[e - nreg];
+        return ((uint64_t)sum_key(colors + idx * C, C) << 32) | (uint32_t)idx;
     }
 };
 
-__global__ void __launch_bounds__(256) i2r_select(I2RArgs a, int64_t M) {
+__device__ __forceinline__ void write_cell(const I2RArgs& a, int64_t gbin, int64_t base, bool filled, int cnt,
+                                           int64_t winner) {
+    for (int c = 0; c < a.C; ++c) a.refmap[gbin * a.C + c] = filled ? a.colors[winner * a.C + c] : 0.f;
+    a.refmask[gbin] = filled ? 1 : 0;
+    if (a.counts) a.counts[gbin] = cnt;
+    if (a.sel_index) a.sel_index[gbin] = filled ? (int32_t)(winner - base) : -1;
+}
+
+// k-th smallest of arr[0..n) (distinct 64-bit values), Hoare quickselect in place
+__device__ __forceinline__ uint64_t quickselect(uint64_t* arr, int n, int k) {
+    int l = 0, r = n - 1;
+    while (l < r) {
+        const uint64_t pivot = arr[(l + r) >> 1];
+        int i = l, j = r;
+        while (i <= j) {
+            while (arr[i] < pivot) ++i;
+            while (arr[j] > pivot) --j;
+            if (i <= j) {
+                const uint64_t t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+                ++i; --j;
+            }
+        }
+        if (k <= j) r = j;
+        else if (k >= i) l = i;
+        else break;
+    }
+    return arr[k];
+}
+
+// One thread per cell: cells with up to SMALL_MAX members and no NaN-angle members, median mode; the others are queued
+// for the warp-per-cell kernel.  The consecutive cells of a CTA own one contiguous run of pairs: it is staged in
+// shared memory with coalesced loads and each thread quickselects its own segment there.
+static constexpr int SELECT_CAP = 6144;  // pairs staged per CTA (48 KB)
+static constexpr int SELECT_THREADS = 128;  // cells per CTA: 128 x SMALL_MAX members always fit the staging buffer
+__global__ void __launch_bounds__(SELECT_THREADS) i2r_select_small(I2RArgs a, int64_t M) {
+    __shared__ uint64_t buf[SELECT_CAP];
+    const int64_t g0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t gbin = g0 + threadIdx.x;
+    const int64_t glast = min(g0 + (int64_t)blockDim.x, M) - 1;
+    const int64_t run0 = a.bin_offset[g0];
+    const int64_t run1 = (int64_t)a.bin_offset[glast] + a.bin_count[glast];
+    const int run = (int)(run1 - run0);
+    const bool staged = run <= SELECT_CAP;
+    if (staged)
+        for (int e = threadIdx.x; e < run; e += blockDim.x) {
+            const uint2 pr = a.pairs[run0 + e];
+            buf[e] = ((uint64_t)pr.x << 32) | pr.y;
+        }
+    __syncthreads();
+    if (gbin >= M) return;
+    const int b = (int)(gbin / a.res2);
+    const int nreg = a.bin_count[gbin], nnan = a.nan_count[b];
+    const int cnt = nreg + nnan;  // (~angle_mask).sum(-1), img2refmap.py:28
+    const int64_t base = a.offsets[b];
+    if (cnt == 0 || cnt < a.min_points) {
+        write_cell(a, gbin, base, false, cnt, 0);
+        return;
+    }
+    if (nnan > 0 || nreg > SMALL_MAX || a.reduce_mode != 0 || !staged) {
+        a.big_list[atomicAdd(a.big_count, 1)] = (int32_t)gbin;
+        return;
+    }
+    uint64_t* seg = buf + (a.bin_offset[gbin] - run0);
+    int nvalid = 0;
+    for (int e = 0; e < nreg; ++e) nvalid += (uint32_t)(seg[e] >> 32) != KEY_NAN;
+    if (nvalid == 0) {
+        write_cell(a, gbin, base, false, cnt, 0);
+        return;
+    }
+    // NaN keys are the largest values, so rank (nvalid - 1) / 2 of the whole segment is the lower median of the valid
+    // members (torch.nanmedian, :31)
+    const uint64_t med = quickselect(seg, nreg, (nvalid - 1) >> 1);
+    write_cell(a, gbin, base, true, cnt, (int64_t)(uint32_t)med);
+}
+
+// one warp per queued cell
+__global__ void __launch_bounds__(256) i2r_select_big(I2RArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t gbin = warp0; gbin < M; gbin += nwarps) {
+    const int nbig = *a.big_count;
+    for (int64_t q = warp0; q < nbig; q += nwarps) {
+        const int64_t gbin = a.big_list[q];
         const int b = (int)(gbin / a.res2);
         const int64_t base = a.offsets[b];
         CellView cv;
@@ -230,75 +387,63 @@ __global__ void __launch_bounds__(256) i2r_select(I2RArgs a, int64_t M) {
         cv.seg = a.pairs + a.bin_offset[gbin];
         cv.nnan = a.nan_count[b];
         cv.nan_list = a.nan_list + base;
-        cv.colors = a.colors + base * a.C;
+        cv.base = base;
+        cv.colors = a.colors;
         cv.C = a.C;
-        const int cnt = cv.nreg + cv.nnan;  // (~angle_mask).sum(-1), img2refmap.py:28
+        const int cnt = cv.nreg + cv.nnan;
 
-        int winner = -1;
+        int64_t winner = -1;
         float mean_c = 0.f;
         bool filled = false;
-        if (cnt > 0 && cnt >= a.min_points) {
-            // valid = members whose sum is not NaN
-            int nvalid = 0;
-            for (int e0 = 0; e0 < cnt; e0 += 32) {
-                int e = e0 + lane;
-                bool v = e < cnt && (uint32_t)(cv.get(e) >> 32) != KEY_NAN;
-                nvalid += __popc(__ballot_sync(0xffffffffu, v));
-            }
-            if (nvalid > 0) {
-                filled = true;
-                if (a.reduce_mode == 0) {
-                    const int k = (nvalid - 1) >> 1;  // lower median, torch.nanmedian (:31)
-                    if (cnt <= 32) {
-                        const uint64_t mine = lane < cnt ? cv.get(lane) : ~0ull;
-                        int rank = 0;
-                        for (int f = 0; f < cnt; ++f) {
-                            uint64_t other = __shfl_sync(0xffffffffu, mine, f);
-                            rank += other < mine;
-                        }
-                        unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rank == k);
-                        winner = (int)(uint32_t)__shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
-                    } else {
-                        for (int e0 = 0; e0 < cnt && winner < 0; e0 += 32) {
-                            const int e = e0 + lane;
-                            const uint64_t mine = e < cnt ? cv.get(e) : ~0ull;
-                            int rank = 0;
-                            for (int f = 0; f < cnt; ++f) rank += cv.get(f) < mine;
-                            unsigned hit = __ballot_sync(0xffffffffu, e < cnt && rank == k);
-                            if (hit) winner = (int)(uint32_t)__shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
-                        }
-                    }
-                } else {
-                    // mean: fp32 sum over valid members in ascending pixel order; lane c owns channel c
-                    int prev = -1;
-                    float acc = 0.f;
-                    for (int r = 0; r < nvalid; ++r) {
-                        int best = 0x7fffffff;
-                        for (int e0 = 0; e0 < cnt; e0 += 32) {
-                            int e = e0 + lane;
-                            if (e < cnt) {
-                                uint64_t el = cv.get(e);
-                                int idx = (int)(uint32_t)el;
-                                if ((uint32_t)(el >> 32) != KEY_NAN && idx > prev) best = min(best, idx);
-                            }
-                        }
-                        for (int d = 16; d; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-                        if (lane < a.C) acc = __fadd_rn(acc, cv.colors[(int64_t)best * a.C + lane]);
-                        prev = best;
-                    }
-                    mean_c = __fdiv_rn(acc, (float)nvalid);
+        // valid = members whose sum is not NaN
+        int nvalid = 0;
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+            int e = e0 + lane;
+            bool v = e < cnt && (uint32_t)(cv.get(e) >> 32) != KEY_NAN;
+            nvalid += __popc(__ballot_sync(0xffffffffu, v));
+        }
+        if (nvalid > 0) {
+            filled = true;
+            if (a.reduce_mode == 0) {
+                const int k = (nvalid - 1) >> 1;  // lower median, torch.nanmedian (:31)
+                for (int e0 = 0; e0 < cnt && winner < 0; e0 += 32) {
+                    const int e = e0 + lane;
+                    const uint64_t mine = e < cnt ? cv.get(e) : ~0ull;
+                    int rank = 0;
+                    for (int f = 0; f < cnt; ++f) rank += cv.get(f) < mine;
+                    unsigned hit = __ballot_sync(0xffffffffu, e < cnt && rank == k);
+                    if (hit) winner = (int64_t)(uint32_t)__shfl_sync(0xffffffffu, mine, __ffs(hit) - 1);
                 }
+            } else {
+                // mean: fp32 sum over valid members in ascending pixel order; lane c owns channel c
+                int64_t prev = -1;
+                float acc = 0.f;
+                for (int r = 0; r < nvalid; ++r) {
+                    long long best = 0x7fffffffffffffffll;
+                    for (int e0 = 0; e0 < cnt; e0 += 32) {
+                        int e = e0 + lane;
+                        if (e < cnt) {
+                            uint64_t el = cv.get(e);
+                            long long idx = (long long)(uint32_t)el;
+                            if ((uint32_t)(el >> 32) != KEY_NAN && idx > prev) best = min(best, idx);
+                        }
+                    }
+                    for (int d = 16; d; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+                    if (lane < a.C) acc = __fadd_rn(acc, cv.colors[best * a.C + lane]);
+                    prev = best;
+                }
+                mean_c = __fdiv_rn(acc, (float)nvalid);
             }
         }
         if (lane < a.C) {
             float v = 0.f;
-            if (filled) v = a.reduce_mode == 0 ? cv.colors[(int64_t)winner * a.C + lane] : mean_c;
+            if (filled) v = a.reduce_mode == 0 ? cv.colors[winner * a.C + lane] : mean_c;
             a.refmap[gbin * a.C + lane] = v;
         }
         if (lane == 0) {
             a.refmask[gbin] = filled ? 1 : 0;
             if (a.counts) a.counts[gbin] = cnt;
-            if (a.sel_index) a.sel_index[gbin] = (filled && a.reduce_mode == 0) ? winner : -1;
+            if (a.sel_index) a.sel_index[gbin] = (filled && a.reduce_mode == 0) ? (int32_t)(winner - base) : -1;
         }
     }
 }
@@ -318,10 +463,13 @@ static size_t i2r_carve(I2RArgs& a, void* ws, int64_t total_n, int B, int res, f
     a.bin_count = c.take<int32_t>(M);
     a.cursor = c.take<int32_t>(M);  // contiguous with bin_count + nan_count + status for one memset
     a.nan_count = c.take<int32_t>(B);
+    a.big_count = c.take<int32_t>(1);
     a.status = c.take<int32_t>(1);
     const size_t zero_end = c.used();
     a.bin_offset = c.take<int32_t>(M);
     a.nan_list = c.take<int32_t>(total_n > 0 ? total_n : 1);
+    a.cell0 = c.take<uint32_t>(total_n > 0 ? total_n : 1);
+    a.big_list = c.take<int32_t>(M);
     a.block_sums = c.take<int32_t>(nblocks + 1);
     a.pair_capacity = total_n * pairs_per_pixel_bound(res, thr);
     a.pairs = c.take<uint2>(a.pair_capacity > 0 ? a.pair_capacity : 1);
@@ -372,30 +520,25 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
     a.min_points = min_points; a.reduce_mode = reduce_mode;
     a.refmap = refmap; a.refmask = refmask; a.counts = counts; a.sel_index = sel_index;
 
-    // bin_count, cursor, nan_count, status are carved first and contiguous (each 256-aligned)
+    // bin_count, cursor, nan_count, big_count, status are carved first and contiguous (each 256-aligned)
     const size_t zero_bytes = (size_t)((char*)a.bin_offset - (char*)a.bin_count);
     DRM_CHECK_CUDA(cudaMemsetAsync(a.bin_count, 0, zero_bytes, st));
     const int64_t nblocks = (M + SCAN_TILE - 1) / SCAN_TILE;
     if (total_n > 0) {
         const unsigned grid = (unsigned)((total_n + 255) / 256);
-        i2r_pixel_pass<0><<<grid, 256, 0, st>>>(a);
+        i2r_hist_pass<<<grid, 256, 0, st>>>(a);
     }
     scan_tiles<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_count, a.bin_offset, a.block_sums, M);
     scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(a.block_sums, (int)nblocks);
     scan_add<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_offset, a.block_sums, M);
     if (total_n > 0) {
         const unsigned grid = (unsigned)((total_n + 255) / 256);
-        i2r_pixel_pass<1><<<grid, 256, 0, st>>>(a);
+        i2r_scatter_pass<<<grid, 256, 0, st>>>(a);
     }
-    {
-        int64_t warps = M;
-        int64_t blocks = (warps * 32 + 255) / 256;
-        const int64_t cap = 148ll * 8 * 16;  // persistent-ish: a few waves of 148 SMs x 8 CTAs
-        if (blocks > cap) blocks = cap;
-        i2r_select<<<(unsigned)blocks, 256, 0, st>>>(a, M);
-    }
+    i2r_select_small<<<(unsigned)((M + SELECT_THREADS - 1) / SELECT_THREADS), SELECT_THREADS, 0, st>>>(a, M);
+    i2r_select_big<<<148 * 4, 256, 0, st>>>(a);
     DRM_CHECK_CUDA(cudaGetLastError());
-    count_launches(total_n > 0 ? 6 : 4);
+    count_launches(total_n > 0 ? 7 : 5);
     return DRM_OK;
 }
 
