@@ -156,7 +156,10 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
         c.thr[2] = 2.4f * powf(cell, 0.8f) * powf(alpha, 0.2f);            // 4 x 4
         c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);  // 8 x 8
         c.thr[4] = 0.f;                                                    // 16 x 16
-        for (int i = 0; i < MAX_LEVELS - 1; ++i) c.thr[i] = level_scale * fmaxf(c.thr[i], 6.f * alpha);
+        // floors: beyond the lobe core (6 alpha), and a few cells away whatever alpha is (coarse refmaps: cell >> alpha)
+        const float cells[MAX_LEVELS - 1] = {3.0f, 2.0f, 1.2f, 0.7f};
+        for (int i = 0; i < MAX_LEVELS - 1; ++i)
+            c.thr[i] = fmaxf(level_scale * fmaxf(c.thr[i], 6.f * alpha), cells[i] * cell);
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
@@ -210,7 +213,7 @@ __device__ __forceinline__ void cell_block_cone(const GatherArgs& g, const Rende
     az = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
     // angular radius: centre-to-corner distance d obeys d^2 <= dth^2 + (dph sin_max)^2 (5 % margin)
     const float dth = 0.5f * (i1 - i0) * g.cell, dph = 0.5f * (j1 - j0) * g.cell * fminf(1.f, st + dth);
-    beta = 1.05f * sqrtf(dth * dth + dph * dph);
+    beta = (dth < 0.1f && dph < 0.1f) ? 1.05f * sqrtf(dth * dth + dph * dph) : dth + dph;  // small blocks: flat-space bound
 }
 
 // Distance, in half-vector space, between a cone of normals and the half vectors h = normalize(v + d) of one map tile;
@@ -227,7 +230,7 @@ __device__ __forceinline__ float tile_distance(const GatherArgs& g, const float*
     sincosf(phc, &sp, &cp);
     // angular radius of the tile: centre-to-corner distance d obeys d^2 <= dth^2 + (dph sin_max)^2 (5 % margin)
     const float dps = dph * fminf(1.f, st + dth);
-    const float gamma = 1.05f * sqrtf(dth * dth + dps * dps);
+    const float gamma = (dth < 0.1f && dps < 0.1f) ? 1.05f * sqrtf(dth * dth + dps * dps) : dth + dps;
     const float dx = st * sp, dy = ct, dz = -st * cp;
     if (g.cull) {
         const float spread = beta + gamma + 0.01f;
@@ -765,7 +768,10 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     if (!(alpha_min > 0.f)) alpha_min = fmaxf(1e-3f, (float)(1.25 * M_PI / He));
     const char* lv = getenv("DRM_RENDER_LEVELS");  // "0" disables the footprint hierarchy (debugging / validation)
     const bool hierarchy = !(lv && lv[0] == '0');
-    float level_scale = 0.3f;  // thresholds of render_setup_kernel are conservative; 0.3 measured (scripts/levels_probe.py)
+    // thresholds of render_setup_kernel are conservative at res 128: 0.3 measured (scripts/levels_probe.py).  Coarser
+    // refmaps have cells much wider than the lobe and the grazing-incidence kink of G1(n.d) at the limb is then the
+    // binding error (scripts/lowres_probe.py): the thresholds grow with the cell size, which costs little there.
+    float level_scale = 0.3f * (float)fmin(10.0, pow(fmax(1.0, (M_PI / res) / (M_PI / 128.0)), 1.5));
     if (const char* ls = getenv("DRM_RENDER_LEVEL_SCALE")) level_scale = (float)atof(ls);
 
     GatherArgs g{};

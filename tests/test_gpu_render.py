@@ -224,3 +224,18 @@ def test_coarse_routes_parity_vs_oracle_full_size(z):
     env = synthetic_envmap(1000, 2000, seed=1007)
     ours = _render(env[None], [z], [VIEWS[3]], 16, 1, channel_first=False)[0]
     assert rel_l2(ours, render_oracle(env, z, VIEWS[3], 16, S=1)) <= TOL
+
+
+@pytest.mark.parametrize("res,S", [(24, 8), (40, 16), (17, 4)])
+def test_hierarchy_partial_blocks_and_far_near_pair(res, S):
+    """Refmap sizes that are not multiples of the far launch's 16-cell blocks (or of the CTA's cell block): the far/near
+    pair and the level schedule against the single-level evaluation, and against the oracle on a window."""
+    env = synthetic_envmap(250, 500, seed=1004)
+    z = Z_CASES["z0_mirror"] if S > 4 else Z_CASES["glossy_metal"]
+    hier = _render(env[None], [z], [VIEWS[2]], res, S, channel_first=False)[0]
+    flat = _with_levels("0", lambda: _render(env[None], [z], [VIEWS[2]], res, S, channel_first=False))[0]
+    assert rel_l2(hier, flat) <= 7e-5
+    win = (res // 2 - 1, res // 2 + 1, res - 3, res)  # includes the last, partial block column
+    ref = render_oracle(env, z, VIEWS[2], res, S=S, window=win)
+    a, b = hier[win[0]:win[1], win[2]:win[3]], ref[win[0]:win[1], win[2]:win[3]]
+    assert rel_l2(a, b) <= TOL
