@@ -156,10 +156,7 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
         c.thr[2] = 2.4f * powf(cell, 0.8f) * powf(alpha, 0.2f);            // 4 x 4
         c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);  // 8 x 8
         c.thr[4] = 0.f;                                                    // 16 x 16
-        // floors: beyond the lobe core (6 alpha), and a few cells away whatever alpha is (coarse refmaps: cell >> alpha)
-        const float cells[MAX_LEVELS - 1] = {3.0f, 2.0f, 1.2f, 0.7f};
-        for (int i = 0; i < MAX_LEVELS - 1; ++i)
-            c.thr[i] = fmaxf(level_scale * fmaxf(c.thr[i], 6.f * alpha), cells[i] * cell);
+        for (int i = 0; i < MAX_LEVELS - 1; ++i) c.thr[i] = level_scale * fmaxf(c.thr[i], 6.f * alpha);  // beyond the core
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
