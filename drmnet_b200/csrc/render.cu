@@ -54,6 +54,7 @@ struct RenderConst {  // per render
     float m, rough, alpha2, inv_a2m1, one_m_a2, eta;
     float base[3], cdiff[3];
     float thr[MAX_LEVELS];  // half-vector-space distance beyond which footprint level k is accurate enough
+    float tk2[MAX_LEVELS];  // the same for one cell: squared chord |n_centre - h|^2 thresholds (cell radius included)
     int env, route;
 };
 
@@ -131,8 +132,9 @@ __global__ void env_coarsen_kernel(const float* __restrict__ env, const float* _
 // level thresholds and the routing of the render's terms to the launches
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N,
-                                    int B, float alpha_min, float cell, float level_scale, float coarse_h,
-                                    float coarse2_h, int coarse_diffuse_ok, RenderConst* __restrict__ rc) {
+                                    int B, float alpha_min, float cell, float level_scale, float near_scale,
+                                    float coarse_h, float coarse2_h, int coarse_diffuse_ok,
+                                    RenderConst* __restrict__ rc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     RenderConst c;
@@ -157,6 +159,11 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
         c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);  // 8 x 8
         c.thr[4] = 0.f;                                                    // 16 x 16
         for (int i = 0; i < MAX_LEVELS - 1; ++i) c.thr[i] = level_scale * fmaxf(c.thr[i], 6.f * alpha);  // beyond the core
+        for (int i = 0; i < MAX_LEVELS; ++i) {
+            // per-cell thresholds are applied exactly (no tile / block slack), hence their own, larger scale
+            const float t = c.thr[i] * (near_scale / level_scale) + 0.75f * cell;  // nodes lie within 0.75 cell of the centre
+            c.tk2[i] = i < MAX_LEVELS - 1 ? t * t : 0.f;
+        }
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
@@ -267,8 +274,9 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
     return g.nlev;
 }
 
-// TERMS: 1 = specular lobe, 2 = diffuse lobe, 3 = both.  COARSE_SRC: the map is the 4x4 energy-centroid coarsening.
-template <int TERMS, bool COARSE_SRC>
+// TERMS: 1 = specular lobe, 2 = diffuse lobe, 3 = both.  COARSE_SRC: the map is an energy-centroid coarsening.
+// NEAR_EXCL: 1x1 lattice only, and (cell, texel) pairs closer than the 1x1 threshold are left to render_near_kernel.
+template <int TERMS, bool COARSE_SRC, bool NEAR_EXCL>
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
 render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs g) {
     constexpr int RAW_FLOATS = TILE_TEXELS * (COARSE_SRC ? COARSE_FLOATS : 3);
@@ -499,7 +507,8 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                     const float sin2 = u2 * (1.f - 0.25f * u2);       // 1 - (n.h)^2
                     const float q = 1.f + sin2 * rc.inv_a2m1;         // cos^2 + sin^2 / alpha^2
                     const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
-                    const float ws = xc * fast_rcp(q * q * (xc + sq));  // D G1(n.d) up to per-slot constants
+                    float ws = xc * fast_rcp(q * q * (xc + sq));      // D G1(n.d) up to per-slot constants
+                    if (NEAR_EXCL) ws = u2 >= rc.tk2[0] ? ws : 0.f;   // the near field belongs to render_near_kernel
                     acc[r][0] += ws * s.y;
                     acc[r][1] += ws * s.z;
                     acc[r][2] += ws * s.w;
@@ -559,13 +568,223 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     }
 }
 
+
+// ---- near field of the specular lobe, one CTA per refmap cell ------------------------------------------------------
+// The tile kernel's block/tile granularity inflates the region that runs on the fine lattices by an order of magnitude
+// for sharp lobes.  Here the split is per (cell, texel): a texel is "near" when the squared chord between the cell's
+// centre normal and its half vector is below tk2[0]; the tile kernel (NEAR_EXCL) skips exactly those pairs, this kernel
+// evaluates them on the lattice their distance asks for (2x2 ... SxS).  Eight warps scan the rows of the window of
+// texels around the mirror direction (coalesced loads straight from the envmap, L2 hits), sort near texels by level
+// into per-warp staging lists in shared memory and, whenever a list holds 32 entries, evaluate them lane-per-texel
+// against that level's lattice nodes (broadcast LDS); partial sums meet in a warp-shuffle tree and a fixed-order
+// reduction over the warps (deterministic).
+static constexpr int NEAR_THREADS = 256, NEAR_WARPS = NEAR_THREADS / 32, NEAR_LIST = 64, NEAR_LEVELS = 4;
+static constexpr int NEAR_NODES = 4 + 16 + 64 + 256;
+
+struct NearArgs {
+    const float* env;
+    const RenderConst* rc;
+    const float *sin_t, *cos_t, *sin_p, *cos_p;
+    float* slab;  // [N][res*res][3]
+    int He, We, N, res, nlev;  // nlev lattices: 2, 4, ... 2^nlev
+    float domega_k, cell;
+    float gl_x[NEAR_LEVELS][16], gl_w[NEAR_LEVELS][16];
+};
+
+__global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArgs g) {
+    extern __shared__ __align__(16) unsigned char near_smem[];
+    float4* node_n = reinterpret_cast<float4*>(near_smem);                       // [NEAR_NODES] normal, n.v
+    float* node_m = reinterpret_cast<float*>(near_smem + NEAR_NODES * 16);       // [NEAR_NODES] weight * constants
+    float4* lists = reinterpret_cast<float4*>(near_smem + NEAR_NODES * 20);      // [warp][level][NEAR_LIST][2]
+    float* wsum = reinterpret_cast<float*>(near_smem + NEAR_NODES * 20 + NEAR_WARPS * NEAR_LEVELS * NEAR_LIST * 32);
+
+    const int k = blockIdx.y;
+    const RenderConst rc = g.rc[k];
+    if (!(rc.route & ROUTE_SPEC_RAW)) return;
+    const int pix = blockIdx.x;
+    const int pi = pix / g.res, pj = pix - pi * g.res;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // lattice nodes of every level: normal, n.v, Gauss-Legendre weight x per-node constants
+    int node_off[NEAR_LEVELS + 1];
+    node_off[0] = 0;
+#pragma unroll
+    for (int l = 0; l < NEAR_LEVELS; ++l) node_off[l + 1] = node_off[l] + (l < g.nlev ? (4 << (2 * l)) : 0);
+    for (int e = tid; e < node_off[g.nlev]; e += NEAR_THREADS) {
+        int l = 0;
+        while (e >= node_off[l + 1]) ++l;
+        const int Sk = 2 << l, node = e - node_off[l];
+        const int a = node / Sk, b = node - a * Sk;
+        const float th = ((float)pi + 0.5f + 0.5f * g.gl_x[l][a]) * g.cell;
+        const float ph = ((float)pj + 0.5f + 0.5f * g.gl_x[l][b]) * g.cell;
+        float st, ct, sp, cp;
+        sincosf(th, &st, &ct);
+        sincosf(ph, &sp, &cp);
+        const float lx = st * cp, lz = st * sp;
+        node_n[e] = make_float4(lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0],
+                                lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1],
+                                lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2], lz);
+        const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
+        node_m[e] = lz > 0.f ? g.gl_w[l][a] * g.gl_w[l][b] / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+    }
+    // centre normal: the node of the tile kernel's 1x1 lattice, same expressions
+    float cnx, cny, cnz;
+    {
+        const float th = ((float)pi + 0.5f + 0.5f * 0.f) * g.cell, ph = ((float)pj + 0.5f + 0.5f * 0.f) * g.cell;
+        float st, ct, sp, cp;
+        sincosf(th, &st, &ct);
+        sincosf(ph, &sp, &cp);
+        const float lx = st * cp, lz = st * sp;
+        cnx = lx * rc.left[0] + ct * rc.upp[0] + lz * rc.vhat[0];
+        cny = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
+        cnz = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
+    }
+    __syncthreads();
+
+    // window of texels that can be near: within 2 * angle(T0) of the mirror direction (reflection doubles angles)
+    const float cv = cnx * rc.vhat[0] + cny * rc.vhat[1] + cnz * rc.vhat[2];
+    const float rx = 2.f * cv * cnx - rc.vhat[0], ry = 2.f * cv * cny - rc.vhat[1], rz = 2.f * cv * cnz - rc.vhat[2];
+    const float dth = 3.14159265f / g.He, dph = 6.2831853f / g.We;
+    const float chord0 = sqrtf(rc.tk2[0]);
+    const float Rd = 4.f * asinf(fminf(1.f, 0.5f * chord0)) + 2.f * (dth + dph) + 0.01f;
+    const float th_r = acosf(fminf(fmaxf(ry, -1.f), 1.f));
+    float ph_r = atan2f(rx, -rz);
+    if (ph_r < 0.f) ph_r += 6.2831853f;
+    const bool whole = Rd >= 3.1f;
+    const int r_lo = whole ? 0 : max(0, (int)floorf((th_r - Rd) / dth));
+    const int r_hi = whole ? g.He - 1 : min(g.He - 1, (int)ceilf((th_r + Rd) / dth));
+    const float cosR = cosf(fminf(Rd, 3.14159265f)), sr = sinf(th_r), cr = cosf(th_r);
+
+    float4* mylist = lists + (size_t)warp * NEAR_LEVELS * NEAR_LIST * 2;
+    int cnt[NEAR_LEVELS] = {0, 0, 0, 0};
+    float tot0 = 0.f, tot1 = 0.f, tot2 = 0.f;
+    const float* src = g.env + (size_t)rc.env * g.He * g.We * 3;
+
+    auto process = [&](int l, int n) {  // lanes < n evaluate their staged texel against every node of lattice l
+        const float4 h = mylist[(l * NEAR_LIST + (lane < n ? lane : 0)) * 2 + 0];
+        const float4 es = mylist[(l * NEAR_LIST + (lane < n ? lane : 0)) * 2 + 1];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        const int n0 = node_off[l], n1 = node_off[l + 1];
+        for (int j = n0; j < n1; ++j) {
+            const float4 nn = node_n[j];
+            const float mlt = node_m[j];
+            const float ex = nn.x - h.x, ey = nn.y - h.y, ez = nn.z - h.z;
+            const float u2 = ex * ex + ey * ey + ez * ez;
+            const float nh = 1.f - 0.5f * u2;
+            const float x = h.w * nh - nn.w;
+            const float xc = fmaxf(x, 0.f);
+            const float sin2 = u2 * (1.f - 0.25f * u2);
+            const float q = 1.f + sin2 * rc.inv_a2m1;
+            const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + rc.alpha2);
+            const float ws = mlt * (xc * fast_rcp(q * q * (xc + sq)));
+            a0 += ws * es.x;
+            a1 += ws * es.y;
+            a2 += ws * es.z;
+        }
+        if (lane < n) { tot0 += a0; tot1 += a1; tot2 += a2; }
+    };
+
+    for (int r = r_lo + warp; r <= r_hi; r += NEAR_WARPS) {
+        const float st = g.sin_t[r], ct = g.cos_t[r];
+        int c_start = 0, ncols = g.We;
+        if (!whole) {
+            const float num = cosR - cr * ct, den = sr * st;
+            if (den > 1e-6f && num > -den) {
+                if (num >= den) continue;  // the row does not reach the window
+                const float dphi = acosf(num / den);
+                ncols = min(g.We, 2 * (int)ceilf(dphi / dph) + 3);
+                c_start = (int)floorf(ph_r / dph) - ncols / 2;
+                c_start = ((c_start % g.We) + g.We) % g.We;
+            }
+        }
+        const float dom = g.domega_k * st;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            const bool in_row = c0 + lane < ncols;
+            int c = c_start + c0 + lane;
+            if (c >= g.We) c -= g.We;
+            int lvl = -1;
+            float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
+            if (in_row) {
+                const float sp = g.sin_p[c], cp = g.cos_p[c];
+                const float dx = st * sp, dy = ct, dz = -st * cp;
+                const float vd = rc.vhat[0] * dx + rc.vhat[1] * dy + rc.vhat[2] * dz;
+                const float len2 = fmaxf(2.f + 2.f * vd, 1e-12f);
+                const float inv_len = rsqrtf(len2);
+                const float len = len2 * inv_len;
+                h4 = make_float4((rc.vhat[0] + dx) * inv_len, (rc.vhat[1] + dy) * inv_len, (rc.vhat[2] + dz) * inv_len, len);
+                const float ex = cnx - h4.x, ey = cny - h4.y, ez = cnz - h4.z;
+                const float u2 = ex * ex + ey * ey + ez * ez;
+                if (u2 < rc.tk2[0]) {
+                    lvl = g.nlev - 1;  // lattice 2^(l+1): the coarsest one whose threshold the distance passes
+                    for (int l = 0; l < g.nlev - 1; ++l)
+                        if (u2 >= rc.tk2[l + 1]) { lvl = l; break; }
+                    const float vh = 0.5f * len;
+                    const float Fd = fresnel_dielectric(vh, rc.eta);
+                    const float mm = fminf(fmaxf(1.f - vh, 0.f), 1.f);
+                    const float sw = (mm * mm) * (mm * mm) * mm;
+                    const float* e = src + ((size_t)r * g.We + c) * 3;
+                    e4.x = e[0] * dom * ((1.f - rc.m) * Fd + rc.m * (rc.base[0] + (1.f - rc.base[0]) * sw));
+                    e4.y = e[1] * dom * ((1.f - rc.m) * Fd + rc.m * (rc.base[1] + (1.f - rc.base[1]) * sw));
+                    e4.z = e[2] * dom * ((1.f - rc.m) * Fd + rc.m * (rc.base[2] + (1.f - rc.base[2]) * sw));
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < NEAR_LEVELS; ++l) {
+                if (l >= g.nlev) break;
+                const unsigned m = __ballot_sync(0xffffffffu, lvl == l);
+                if (!m) continue;
+                if (lvl == l) {
+                    const int pos = cnt[l] + __popc(m & ((1u << lane) - 1u));
+                    mylist[(l * NEAR_LIST + pos) * 2 + 0] = h4;
+                    mylist[(l * NEAR_LIST + pos) * 2 + 1] = e4;
+                }
+                cnt[l] += __popc(m);
+                __syncwarp();
+                if (cnt[l] >= 32) {
+                    process(l, 32);
+                    // move the overflow (entries 32 .. cnt-1) to the front
+                    const int rest = cnt[l] - 32;
+                    float4 t0, t1;
+                    if (lane < rest) {
+                        t0 = mylist[(l * NEAR_LIST + 32 + lane) * 2 + 0];
+                        t1 = mylist[(l * NEAR_LIST + 32 + lane) * 2 + 1];
+                    }
+                    __syncwarp();
+                    if (lane < rest) {
+                        mylist[(l * NEAR_LIST + lane) * 2 + 0] = t0;
+                        mylist[(l * NEAR_LIST + lane) * 2 + 1] = t1;
+                    }
+                    cnt[l] = rest;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NEAR_LEVELS; ++l)
+        if (l < g.nlev && cnt[l] > 0) process(l, cnt[l]);
+
+    for (int d = 16; d; d >>= 1) {
+        tot0 += __shfl_xor_sync(0xffffffffu, tot0, d);
+        tot1 += __shfl_xor_sync(0xffffffffu, tot1, d);
+        tot2 += __shfl_xor_sync(0xffffffffu, tot2, d);
+    }
+    if (lane == 0) { wsum[warp * 3 + 0] = tot0; wsum[warp * 3 + 1] = tot1; wsum[warp * 3 + 2] = tot2; }
+    __syncthreads();
+    if (tid < 3) {
+        float v = 0.f;
+        for (int w = 0; w < NEAR_WARPS; ++w) v += wsum[w * 3 + tid];
+        g.slab[((size_t)k * g.res * g.res + pix) * 3 + tid] = v;
+    }
+}
+
 struct SlabDesc {
     const float* base;
     int splits, route_mask;
 };
 
 // out = sum over the launches that served the render and over their texel splits, in fixed order (deterministic)
-__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4,
+__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4, SlabDesc s5,
                                       const RenderConst* __restrict__ rc, float* __restrict__ out, int N, int res,
                                       int channel_first) {
     const size_t total = (size_t)N * res * res * 3;
@@ -576,9 +795,9 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
     const size_t k = o / 3 / ((size_t)res * res);
     const int route = rc[k].route;
     float v = 0.f;
-    const SlabDesc slabs[5] = {s0, s1, s2, s3, s4};
+    const SlabDesc slabs[6] = {s0, s1, s2, s3, s4, s5};
 #pragma unroll
-    for (int l = 0; l < 5; ++l)
+    for (int l = 0; l < 6; ++l)
         if (slabs[l].base && (route & slabs[l].route_mask))
             for (int s = 0; s < slabs[l].splits; ++s) v += slabs[l].base[(size_t)s * total + o];
     const size_t idx = channel_first ? (k * 3 + c) * res * res + pix : o;
@@ -626,9 +845,11 @@ struct RenderLayout {
     bool coarse_enabled, coarse_diffuse_ok;
     float coarse_h, coarse2_h;
     bool far_pair;  // the raw-map launch is split into a far launch (16x16-cell blocks) and a near launch
+    bool pow2;      // S in {2,4,8,16}: the footprint hierarchy (and the per-cell near-field kernel) applies
     RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
     RenderConst* rc;
-    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_diff, *slab_coarse, *slab_coarse2;
+    float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_near, *slab_diff, *slab_coarse,
+        *slab_coarse2;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -641,6 +862,7 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     const char* cv = getenv("DRM_RENDER_COARSE");  // "0" disables the coarse-map routes (debugging / validation)
     L.coarse_enabled = !(cv && cv[0] == '0') && He >= 8 * COARSE && We >= 8 * COARSE;
     L.coarse_diffuse_ok = L.coarse_enabled && L.coarse_h <= 0.0135f;
+    L.pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
     L.far_pair = (S == 8 || S == 16) && res >= FAR_EDGE;
     L.raw = make_plan(N, He, We, res, S, default_slots(S));
     L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE));
@@ -657,7 +879,8 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
     L.coarse2_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc2 * L.Wc2 * COARSE_FLOATS : 1);
     L.slab_raw = c.take<float>(slice * L.raw.splits);
-    L.slab_far = c.take<float>(L.far_pair ? slice * L.far.splits : 1);
+    L.slab_far = c.take<float>(L.pow2 ? slice * L.far.splits : 1);
+    L.slab_near = c.take<float>(L.pow2 ? slice : 1);
     L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     L.slab_coarse2 = c.take<float>(L.coarse_enabled ? slice * L.coarse2.splits : 1);
@@ -725,14 +948,14 @@ static int make_tensor_map(CUtensorMap* tmap, const float* base, int B, int Hm, 
     return DRM_OK;
 }
 
-template <int TERMS, bool COARSE_SRC>
+template <int TERMS, bool COARSE_SRC, bool NEAR_EXCL = false>
 static int launch_gather(const GatherArgs& g, const CUtensorMap& tmap, const RenderPlan& p, int N, cudaStream_t st) {
     const size_t raw_floats = (size_t)TILE_TEXELS * (COARSE_SRC ? COARSE_FLOATS : 3);
     const size_t smem = 2 * raw_floats * sizeof(float) + TILE_TEXELS * REC_FLOATS * sizeof(float) + 16 + 64 + MAX_LIST * 3;
-    DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<TERMS, COARSE_SRC>,
+    DRM_CHECK_CUDA(cudaFuncSetAttribute(render_gather_kernel<TERMS, COARSE_SRC, NEAR_EXCL>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.tiles_x * p.tiles_y, N, p.splits);
-    render_gather_kernel<TERMS, COARSE_SRC><<<grid, GATHER_THREADS, smem, st>>>(tmap, g);
+    render_gather_kernel<TERMS, COARSE_SRC, NEAR_EXCL><<<grid, GATHER_THREADS, smem, st>>>(tmap, g);
     count_launches(1);
     return DRM_OK;
 }
@@ -782,7 +1005,9 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
 
     const int tb = 128;
     render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(L.sin_t, L.cos_t, L.sin_p, L.cos_p, He, We);
-    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale,
+    float near_scale = 2.f * level_scale;
+    if (const char* ns = getenv("DRM_RENDER_NEAR_SCALE")) near_scale = (float)atof(ns);
+    render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale, near_scale,
                                                          L.coarse_enabled ? L.coarse_h : 0.f,
                                                          L.coarse_enabled ? L.coarse2_h : 0.f, L.coarse_diffuse_ok ? 1 : 0,
                                                          L.rc);
@@ -804,7 +1029,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         a.G = p.G;
     };
     int rc_code;
-    bool used_far = false;
+    bool used_far = false, near_mode = false;
     // ---- launches on the raw map: specular lobe only, and both lobes -------------------------------------------------
     {
         GatherArgs a = g;
@@ -817,23 +1042,47 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         a.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
         if (a.use_tma && (rc_code = make_tensor_map(&tmap, env, B, He, We, 3)) != DRM_OK) return rc_code;
         const bool pair = L.far_pair && hierarchy;
-        a.part = pair ? PART_NEAR : PART_ALL;
-        a.route_mask = ROUTE_SPEC_RAW;
-        if ((rc_code = launch_gather<1, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
+        const char* nv = getenv("DRM_RENDER_NEAR");  // "0": block/tile level schedule instead of the per-cell near kernel
+        // measured (scripts/levels_probe.py): 2.4x / 1.6x faster than the block schedule for the 16x16 / 8x8 footprints,
+        // slower for 4x4 and 2x2 whose windows are too wide to scan once per cell
+        near_mode = L.pow2 && S >= 8 && hierarchy && !(nv && nv[0] == '0');
+        // far half of a pair / NEAR_EXCL launch: 16x16-cell blocks, 1x1 lattice, 4 slots per cell share each tile
+        GatherArgs f = a;
+        f.slab = L.slab_far;
+        fill_plan(f, L.far);
+        set_levels(f, 1, false);
+        if (near_mode) {
+            // specular-only renders: every (cell, texel) pair beyond the 1x1 threshold here, the rest per cell below
+            f.part = PART_ALL; f.route_mask = ROUTE_SPEC_RAW;
+            if ((rc_code = launch_gather<1, false, true>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            NearArgs n{};
+            n.env = env; n.rc = L.rc; n.sin_t = L.sin_t; n.cos_t = L.cos_t; n.sin_p = L.sin_p; n.cos_p = L.cos_p;
+            n.slab = L.slab_near; n.He = He; n.We = We; n.N = N; n.res = res;
+            n.domega_k = g.domega_k; n.cell = g.cell;
+            n.nlev = 0;
+            for (int sk = 2; sk <= S; sk *= 2) {
+                gauss_legendre(sk, n.gl_x[n.nlev], n.gl_w[n.nlev]);
+                ++n.nlev;
+            }
+            const size_t nsmem = NEAR_NODES * 20 + (size_t)NEAR_WARPS * NEAR_LEVELS * NEAR_LIST * 32 + NEAR_WARPS * 3 * 4;
+            DRM_CHECK_CUDA(cudaFuncSetAttribute(render_near_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+            render_near_kernel<<<dim3(res * res, N), NEAR_THREADS, nsmem, st>>>(n);
+            count_launches(1);
+        } else {
+            a.part = pair ? PART_NEAR : PART_ALL;
+            a.route_mask = ROUTE_SPEC_RAW;
+            if ((rc_code = launch_gather<1, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
+            if (pair) {
+                f.part = PART_FAR; f.route_mask = ROUTE_SPEC_RAW;
+                if ((rc_code = launch_gather<1, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            }
+        }
         if (!L.coarse_diffuse_ok) {  // otherwise no render is routed to BOTH_RAW
+            a.part = pair ? PART_NEAR : PART_ALL;
             a.route_mask = ROUTE_BOTH_RAW;
             if ((rc_code = launch_gather<3, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
-        }
-        if (pair) {
-            // far half: 16x16-cell blocks, 1x1 lattice, 4 slots per cell share each tile's texels
-            GatherArgs f = a;
-            f.part = PART_FAR; f.slab = L.slab_far;
-            fill_plan(f, L.far);
-            set_levels(f, 1, false);
-            f.route_mask = ROUTE_SPEC_RAW;
-            if ((rc_code = launch_gather<1, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
-            if (!L.coarse_diffuse_ok) {
-                f.route_mask = ROUTE_BOTH_RAW;
+            if (pair) {
+                f.part = PART_FAR; f.route_mask = ROUTE_BOTH_RAW;
                 if ((rc_code = launch_gather<3, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
             }
         }
@@ -872,13 +1121,15 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         if ((rc_code = launch_gather<3, true>(a2, tmap2, L.coarse2, N, st)) != DRM_OK) return rc_code;
     }
     {
-        SlabDesc s0{L.slab_raw, L.raw.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
+        SlabDesc s0{L.slab_raw, L.raw.splits, (near_mode ? 0 : ROUTE_SPEC_RAW) | ROUTE_BOTH_RAW};
         SlabDesc s1{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff.splits, ROUTE_DIFF_COARSE};
         SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
-        SlabDesc s3{used_far ? L.slab_far : nullptr, L.far.splits, ROUTE_SPEC_RAW | ROUTE_BOTH_RAW};
+        SlabDesc s3{(used_far || near_mode) ? L.slab_far : nullptr, L.far.splits,
+                    ((used_far || near_mode) ? ROUTE_SPEC_RAW : 0) | (used_far ? ROUTE_BOTH_RAW : 0)};
+        SlabDesc s5{near_mode ? L.slab_near : nullptr, 1, ROUTE_SPEC_RAW};
         const size_t total = (size_t)N * res * res * 3;
         SlabDesc s4{L.coarse_enabled ? L.slab_coarse2 : nullptr, L.coarse2.splits, ROUTE_BOTH_COARSE2};
-        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, L.rc, out, N, res, channel_first);
+        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, s5, L.rc, out, N, res, channel_first);
         count_launches(1);
     }
     DRM_CHECK_CUDA(cudaGetLastError());

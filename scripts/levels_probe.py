@@ -1,4 +1,5 @@
-"""Footprint-hierarchy error and time against the single-level brute force of the same canonical sum (diagnostic, GPU)."""
+"""Footprint-hierarchy error and time against the single-level brute force of the same canonical sum (diagnostic, GPU).
+The scales given on the command line are values of DRM_RENDER_NEAR_SCALE (per-cell near-field thresholds)."""
 import os, sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -9,7 +10,7 @@ from drmnet_b200.synth import synthetic_envmap
 dev = "cuda:0"
 def run(env, z, v, S, levels, scale=1.0):
     os.environ["DRM_RENDER_LEVELS"] = "1" if levels else "0"
-    os.environ["DRM_RENDER_LEVEL_SCALE"] = str(scale)
+    os.environ["DRM_RENDER_NEAR_SCALE"] = str(scale)
     torch.cuda.synchronize(); t = time.time()
     o = render_batch(env, z, v, res=128, footprint_S=S)
     torch.cuda.synchronize()
