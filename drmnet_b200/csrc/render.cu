@@ -809,8 +809,9 @@ struct RenderPlan {
 };
 
 // slots per cell: S^2, raised to 16 for the 2x2 and 4x4 lattices so that their blocks are 8x8 cells (a tighter cone of
-// normals sends more tiles to the coarse levels)
-static int default_slots(int S) { return (S == 2 || S == 4) ? 16 : S * S; }
+// normals sends more tiles to the coarse levels) and to 4 for the 1x1 lattice (16x16-cell blocks cull a third of the
+// tiles that 32x32-cell blocks would visit)
+static int default_slots(int S) { return S == 1 ? 4 : (S == 2 || S == 4) ? 16 : S * S; }
 
 static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
     RenderPlan p;
