@@ -827,9 +827,9 @@ static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
     p.ttiles_x = (Wm + TT - 1) / TT;
     p.ttiles_y = (Hm + TT - 1) / TT;
     const long ctas = (long)p.tiles_x * p.tiles_y * N;
-    // six waves of two resident CTAs per SM: a launch may serve only the fraction of the N renders routed to it (the
+    // twelve waves of two resident CTAs per SM: a launch may serve only the fraction of the N renders routed to it (the
     // routing is decided on the device), so the grid is over-split to keep the GPU full and balanced in that case
-    const long want = 148L * 2 * 6;
+    const long want = 148L * 2 * 12;
     long s = (want + ctas - 1) / ctas;
     const long ntiles = (long)p.ttiles_x * p.ttiles_y;
     const long smax = ntiles / 4 > 0 ? ntiles / 4 : 1;
