@@ -92,40 +92,63 @@ __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, f
     }
 }
 
-// K3: F x F-texel energy-centroid coarsening (F = 4 and 2).  Cell = {unit centroid direction (luminance * solid-angle weighted),
-// sum of radiance * solid angle per channel}: placing the cell's energy at its centroid cancels the first-order error
-// of evaluating a smooth lobe once per cell.
+// K3: energy-centroid coarsenings, 2x2 and 4x4 texels per cell, in one pass over the envmaps this call uses.
+// Cell = {unit centroid direction (luminance * solid-angle weighted), sum of radiance * solid angle per channel}: placing
+// the cell's energy at its centroid cancels the first-order error of evaluating a smooth lobe once per cell.
+// One thread per 4x4 cell: it writes its four 2x2 cells and their union.
+__global__ void env_mark_used_kernel(const RenderConst* __restrict__ rc, int N, int* __restrict__ used) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) used[rc[k].env] = 1;
+}
+
 __global__ void env_coarsen_kernel(const float* __restrict__ env, const float* __restrict__ sin_t,
                                    const float* __restrict__ cos_t, const float* __restrict__ sin_p,
-                                   const float* __restrict__ cos_p, int B, int He, int We, int Hc, int Wc, int F,
-                                   float domega_k, float* __restrict__ coarse) {
+                                   const float* __restrict__ cos_p, const int* __restrict__ used, int B, int He, int We,
+                                   int Hc, int Wc, int Hc2, int Wc2, float domega_k, float* __restrict__ coarse4,
+                                   float* __restrict__ coarse2) {
     const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (cell >= (long)B * Hc * Wc) return;
     const int C = (int)(cell % Wc), R = (int)((cell / Wc) % Hc), b = (int)(cell / ((long)Wc * Hc));
+    if (!used[b]) return;
     const float* src = env + (size_t)b * He * We * 3;
-    float m0 = 0.f, m1 = 0.f, m2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for (int dr = 0; dr < F; ++dr) {
-        const int r = R * F + dr;
-        if (r >= He) break;
-        const float st = sin_t[r], ct = cos_t[r], dom = domega_k * st;
-        for (int dc = 0; dc < F; ++dc) {
-            const int c = C * F + dc;
-            if (c >= We) break;
-            const float* e = src + ((size_t)r * We + c) * 3;
-            const float er = e[0] * dom, eg = e[1] * dom, eb = e[2] * dom;
-            const float dx = st * sin_p[c], dy = ct, dz = -st * cos_p[c];
-            const float w = er + eg + eb;
-            m0 += er; m1 += eg; m2 += eb;
-            cx += w * dx; cy += w * dy; cz += w * dz;
-            gx += dom * dx; gy += dom * dy; gz += dom * dz;  // geometric centre, used when the cell is black
+    float M0 = 0.f, M1 = 0.f, M2 = 0.f, CX = 0.f, CY = 0.f, CZ = 0.f, GX = 0.f, GY = 0.f, GZ = 0.f;
+    for (int sr = 0; sr < 2; ++sr)
+        for (int sc = 0; sc < 2; ++sc) {
+            const int R2 = R * 2 + sr, C2 = C * 2 + sc;
+            if (R2 >= Hc2 || C2 >= Wc2) continue;
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+            for (int dr = 0; dr < 2; ++dr) {
+                const int r = R2 * 2 + dr;
+                if (r >= He) break;
+                const float st = sin_t[r], ct = cos_t[r], dom = domega_k * st;
+                for (int dc = 0; dc < 2; ++dc) {
+                    const int c = C2 * 2 + dc;
+                    if (c >= We) break;
+                    const float* e = src + ((size_t)r * We + c) * 3;
+                    const float er = e[0] * dom, eg = e[1] * dom, eb = e[2] * dom;
+                    const float dx = st * sin_p[c], dy = ct, dz = -st * cos_p[c];
+                    const float w = er + eg + eb;
+                    m0 += er; m1 += eg; m2 += eb;
+                    cx += w * dx; cy += w * dy; cz += w * dz;
+                    gx += dom * dx; gy += dom * dy; gz += dom * dz;  // geometric centre, used when the cell is black
+                }
+            }
+            M0 += m0; M1 += m1; M2 += m2;
+            CX += cx; CY += cy; CZ += cz;
+            GX += gx; GY += gy; GZ += gz;
+            float n2 = cx * cx + cy * cy + cz * cz;
+            if (!(n2 > 1e-30f)) { cx = gx; cy = gy; cz = gz; n2 = cx * cx + cy * cy + cz * cz; }
+            const float inv = rsqrtf(fmaxf(n2, 1e-38f));
+            float* o = coarse2 + (((size_t)b * Hc2 + R2) * Wc2 + C2) * COARSE_FLOATS;
+            o[0] = cx * inv; o[1] = cy * inv; o[2] = cz * inv;
+            o[3] = m0; o[4] = m1; o[5] = m2;
         }
-    }
-    float n2 = cx * cx + cy * cy + cz * cz;
-    if (!(n2 > 1e-30f)) { cx = gx; cy = gy; cz = gz; n2 = cx * cx + cy * cy + cz * cz; }
+    float n2 = CX * CX + CY * CY + CZ * CZ;
+    if (!(n2 > 1e-30f)) { CX = GX; CY = GY; CZ = GZ; n2 = CX * CX + CY * CY + CZ * CZ; }
     const float inv = rsqrtf(fmaxf(n2, 1e-38f));
-    float* o = coarse + (size_t)cell * COARSE_FLOATS;
-    o[0] = cx * inv; o[1] = cy * inv; o[2] = cz * inv;
-    o[3] = m0; o[4] = m1; o[5] = m2;
+    float* o = coarse4 + (size_t)cell * COARSE_FLOATS;
+    o[0] = CX * inv; o[1] = CY * inv; o[2] = CZ * inv;
+    o[3] = M0; o[4] = M1; o[5] = M2;
 }
 
 // clip z to [0,1] (mitsuba3_utils.py:239,242), derive the BSDF constants, the camera frame (:235-236), the footprint
@@ -849,6 +872,7 @@ struct RenderLayout {
     bool pow2;      // S in {2,4,8,16}: the footprint hierarchy (and the per-cell near-field kernel) applies
     RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
     RenderConst* rc;
+    int* env_used;
     float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_near, *slab_diff, *slab_coarse,
         *slab_coarse2;
 };
@@ -877,6 +901,7 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.cos_t = c.take<float>(He);
     L.sin_p = c.take<float>(We);
     L.cos_p = c.take<float>(We);
+    L.env_used = c.take<int>(B);
     L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
     L.coarse2_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc2 * L.Wc2 * COARSE_FLOATS : 1);
     L.slab_raw = c.take<float>(slice * L.raw.splits);
@@ -1014,13 +1039,12 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                                                          L.rc);
     count_launches(2);
     if (L.coarse_enabled) {
+        DRM_CHECK_CUDA(cudaMemsetAsync(L.env_used, 0, sizeof(int) * B, st));
+        env_mark_used_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(L.rc, N, L.env_used);
         const long cells = (long)B * L.Hc * L.Wc;
-        env_coarsen_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, B, He,
-                                                                            We, L.Hc, L.Wc, COARSE, g.domega_k, L.coarse_map);
-        const long cells2 = (long)B * L.Hc2 * L.Wc2;
-        env_coarsen_kernel<<<(unsigned)((cells2 + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, B, He,
-                                                                             We, L.Hc2, L.Wc2, COARSE2, g.domega_k,
-                                                                             L.coarse2_map);
+        env_coarsen_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, L.env_used,
+                                                                            B, He, We, L.Hc, L.Wc, L.Hc2, L.Wc2, g.domega_k,
+                                                                            L.coarse_map, L.coarse2_map);
         count_launches(2);
     }
 
