@@ -34,6 +34,18 @@ ALG_BYTES_PER_REFMAP = HE * WE * 3 * 4 + RES * RES * 3 * 4 + 40  # 24
 METRIC = "refmaps rendered/sec (128^2, 2000x1000 envmap)"
 
 
+def measured_traffic(batch, footprint):
+    """DRAM bytes of one step from the committed ncu capture (profiles/r1_traffic.json), for the workload it was taken on."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        if d["workload"] == {"batch_per_gpu": batch, "footprint": footprint}:
+            return d["dram_bytes_per_step"]
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -282,7 +294,8 @@ def main():
                        "l2": "inputs larger than L2 (1.5 GB of envmaps per GPU)", "parallelism": f"dp{world}",
                        "collective": "all_gather of rendered refmaps" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(batch, args.footprint), "algorithmic_bytes_per_step": batch * ALG_BYTES_PER_REFMAP,
+                         "peak_source": peak_src,
                          "note": "kernel is FP32/MUFU-pipe bound (FMA pipe 72% busy, DRAM 0.01%: profiles/), not HBM bound; "
                                  "see DESIGN.md 5"},
             "canonical_sum": {"pairs_per_step": pairs, "pairs_per_s_equivalent": pairs / (ms_per_step / 1e3),
