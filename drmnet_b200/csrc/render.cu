@@ -12,13 +12,15 @@
 // tile into per-texel records (half vector, Fresnel-weighted radiance * solid angle, retro-reflection factor) that are
 // pixel independent, then every thread gathers records for its 4 sub-normal slots from shared memory (LDS.128).
 //
-// Three controlled reductions of the pair count keep the result within ~5e-5 of the full sum (tests):
+// Controlled reductions of the pair count keep the result within ~6e-5 of the full sum (tests):
 //   * footprint levels: a texel tile far (in half-vector space) from the CTA's normals is integrated over the cell
 //     with a coarser Gauss-Legendre lattice (16x16 -> 8x8 -> 4x4 -> 2x2 -> 1x1); the slots freed by the coarser
 //     lattice split the tile's texels among themselves, so no thread idles;
+//   * for the 8x8 and 16x16 footprints the near field is split off per (cell, texel) and evaluated by
+//     render_near_kernel (one CTA per cell, window scan around the mirror direction), the tile kernel keeps the 1x1 rest;
 //   * the diffuse lobe, which varies on the scale of a radian, is gathered from a 4x4-texel energy-centroid coarsening
 //     of the envmap (built per call by env_coarsen_kernel) when those cells are small enough;
-//   * a very rough specular lobe (alpha >= 4x4-cell size / 0.026) is gathered from the same coarsening.
+//   * a rough specular lobe (alpha >= cell size / 0.018) is gathered from the 4x4 or the 2x2 coarsening.
 // The kernel is bound by the FP32/MUFU pipes (about 22 instructions per (slot, texel) pair for the specular lobe, 14
 // for the diffuse one), not by HBM: each envmap byte is reused by every slot of the render out of L2.
 #include <math.h>
