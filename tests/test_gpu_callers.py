@@ -130,3 +130,28 @@ def test_config3_pipeline_render_shade_scatter_round_trip():
     ok = (back >= lo * (1 - 1e-5)) & (back <= hi * (1 + 1e-5))
     assert ok[filled].all()
     assert rel_l2(back[filled], src[filled]) < 0.05
+
+
+def test_round_trip_render_then_mirmap2envmap_recovers_the_envmap():
+    """r0toenvmap(render(z0)) ~ envmap on the hemisphere the mirror sphere shows sharply.  Ties the renderer's
+    geometry (rows, columns, left/right, envmap azimuth) to the reference's mirmap2envmap, whose kernel is pinned by a
+    golden of the reference's own output."""
+    from drmnet_b200.callers import r0toenvmap
+    from drmnet_b200.renderer import render_batch
+    from drmnet_b200.synth import Z0, envmap_directions
+    g = torch.Generator().manual_seed(11)
+    low = torch.exp(0.8 * torch.randn(1, 3, 8, 16, generator=g))
+    low = torch.cat([low, low[..., :1]], -1)  # periodic in azimuth
+    env = torch.nn.functional.interpolate(low, size=(128, 257), mode="bicubic", align_corners=True)[0, :, :, :256]
+    env = env.clamp_min(0.05).permute(1, 2, 0).contiguous().to(DEV)  # smooth HDR-ish map [128,256,3]
+    z0 = torch.tensor([list(Z0)])
+    view = torch.tensor([[0.0, 0.0, 1.0]])
+    r0 = render_batch(env[None], z0, view, res=128, footprint_S=4)
+    basis = render_batch(torch.ones_like(env)[None], z0, view, res=128, footprint_S=4)[0]
+    rec = r0toenvmap(r0, basis, (128, 256))[0]  # [128,256,3]
+    d = envmap_directions(128, 256, device=DEV)
+    front = d[..., 2] > 0.3  # reflected off normals within ~50 degrees of the viewer: well away from the limb
+    ok = rel_l2(rec[front].cpu().numpy(), env[front].cpu().numpy())
+    assert ok < 0.1, ok
+    for wrong in (env.flip(1), env.flip(0), torch.roll(env, 64, dims=1)):
+        assert rel_l2(rec[front].cpu().numpy(), wrong[front].cpu().numpy()) > 3 * ok
