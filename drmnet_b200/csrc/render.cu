@@ -34,7 +34,7 @@ namespace drm {
 static constexpr int GATHER_THREADS = 256;
 static constexpr int SUBS_PER_THREAD = 4;
 static constexpr int SLOTS = GATHER_THREADS * SUBS_PER_THREAD;  // sub-normal slots per CTA
-static constexpr int TT = 32;                                   // tile edge in texels (or coarse cells)
+static constexpr int TT = 32;                                   // largest tile edge in texels (or coarse cells)
 static constexpr int TILE_TEXELS = TT * TT;
 static constexpr int REC_FLOATS = 12;
 static constexpr int MAX_LEVELS = 5;   // footprint lattices 1,2,4,8,16 per axis
@@ -70,6 +70,7 @@ struct GatherArgs {
     int tile_w, tile_h, tiles_x, tiles_y;
     int ttiles_x, ttiles_y, splits;
     int use_tma, cull, route_mask;
+    int tt;                    // tile edge in texels of this launch's map (8, 16 or 32)
     int G;                     // sub-normal slots per refmap cell (a multiple of S*S)
     int part;                  // PART_ALL, or the far / near half of a launch pair (see far_tile)
     int far_edge;              // edge, in cells, of the blocks the far launch works on
@@ -251,7 +252,7 @@ __device__ __forceinline__ void cell_block_cone(const GatherArgs& g, const Rende
 __device__ __forceinline__ float tile_distance(const GatherArgs& g, const float* __restrict__ vhat, int tile, float ax,
                                                float ay, float az, float beta) {
     const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
-    const int r0 = ty * TT, r1 = min(r0 + TT, g.Hm), c0 = tx * TT, c1 = min(c0 + TT, g.Wm);
+    const int r0 = ty * g.tt, r1 = min(r0 + g.tt, g.Hm), c0 = tx * g.tt, c1 = min(c0 + g.tt, g.Wm);
     const float dth = 0.5f * (r1 - r0) * g.dth_cell, dph = 0.5f * (c1 - c0) * g.dph_cell;
     const float thc = fminf(0.5f * (r0 + r1) * g.dth_cell, 3.14159265f), phc = 0.5f * (c0 + c1) * g.dph_cell;
     float st, ct, sp, cp;
@@ -304,9 +305,10 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
 template <int TERMS, bool COARSE_SRC, bool NEAR_EXCL>
 __global__ void __launch_bounds__(GATHER_THREADS, 2)
 render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs g) {
-    constexpr int RAW_FLOATS = TILE_TEXELS * (COARSE_SRC ? COARSE_FLOATS : 3);
-    constexpr int ROW_FLOATS = TT * (COARSE_SRC ? COARSE_FLOATS : 3);
+    constexpr int CELL_FLOATS = COARSE_SRC ? COARSE_FLOATS : 3;
+    constexpr int RAW_FLOATS = TILE_TEXELS * CELL_FLOATS;  // stage size for the largest tile
     constexpr bool SPEC = (TERMS & 1) != 0, DIFF = (TERMS & 2) != 0;
+    const int tt = g.tt, tile_texels = tt * tt, row_floats = tt * CELL_FLOATS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* raw0 = reinterpret_cast<float*>(smem_raw);
     float4* rec = reinterpret_cast<float4*>(smem_raw + 2 * RAW_FLOATS * sizeof(float));
@@ -394,8 +396,8 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
     auto issue = [&](int e, int stage) {
         const int tile = tbeg + list[e] * tstep;
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
-        mbar_arrive_expect_tx(&bars[stage], RAW_FLOATS * sizeof(float));
-        tma_load_3d(raw0 + stage * RAW_FLOATS, &tmap, &bars[stage], tx * ROW_FLOATS, ty * TT, rc.env);
+        mbar_arrive_expect_tx(&bars[stage], tile_texels * CELL_FLOATS * sizeof(float));
+        tma_load_3d(raw0 + stage * RAW_FLOATS, &tmap, &bars[stage], tx * row_floats, ty * tt, rc.env);
     };
     if (g.use_tma && tid == 0) {
         if (0 < nlist) issue(0, 0);
@@ -453,34 +455,32 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
             mbar_wait(&bars[stage], (it >> 1) & 1);
         } else {
             // plain-load staging for maps whose row pitch is not a multiple of 16 bytes
-            const int row_floats = g.Wm * (COARSE_SRC ? COARSE_FLOATS : 3);
-            const float* src = g.src + (size_t)rc.env * g.Hm * row_floats;
-            for (int e = tid; e < RAW_FLOATS; e += GATHER_THREADS) {
-                const int lr = e / ROW_FLOATS, lc = e - lr * ROW_FLOATS;
-                const int r = ty * TT + lr, c = tx * ROW_FLOATS + lc;
-                raw[e] = (r < g.Hm && c < row_floats) ? src[(size_t)r * row_floats + c] : 0.f;
+            const int map_row = g.Wm * CELL_FLOATS;
+            const float* src = g.src + (size_t)rc.env * g.Hm * map_row;
+            for (int e = tid; e < tile_texels * CELL_FLOATS; e += GATHER_THREADS) {
+                const int lr = e / row_floats, lc = e - lr * row_floats;
+                const int r = ty * tt + lr, c = tx * row_floats + lc;
+                raw[e] = (r < g.Hm && c < map_row) ? src[(size_t)r * map_row + c] : 0.f;
             }
             __syncthreads();
         }
 
         // ---- transform: raw tile -> pixel-independent records {h, |v+d|, Rr, E dOmega F_c, E dOmega} -----------------
-#pragma unroll
-        for (int u = 0; u < TILE_TEXELS / GATHER_THREADS; ++u) {
-            const int t = u * GATHER_THREADS + tid;
-            const int lr = t / TT, lc = t - lr * TT;
+        for (int t = tid; t < tile_texels; t += GATHER_THREADS) {
+            const int lr = t / tt, lc = t - lr * tt;
             float dx, dy, dz, er, eg, eb;
             if (COARSE_SRC) {
-                const float* cellp = raw + lr * ROW_FLOATS + lc * COARSE_FLOATS;
+                const float* cellp = raw + lr * row_floats + lc * COARSE_FLOATS;
                 dx = cellp[0]; dy = cellp[1]; dz = cellp[2];
                 er = cellp[3]; eg = cellp[4]; eb = cellp[5];
             } else {
-                const int r = min(ty * TT + lr, g.He - 1), c = min(tx * TT + lc, g.We - 1);
+                const int r = min(ty * tt + lr, g.He - 1), c = min(tx * tt + lc, g.We - 1);
                 const float st = g.sin_t[r], ct = g.cos_t[r], sp = g.sin_p[c], cp = g.cos_p[c];
                 dx = st * sp; dy = ct; dz = -st * cp;
                 const float dom = g.domega_k * st;
-                er = raw[lr * ROW_FLOATS + lc * 3 + 0] * dom;
-                eg = raw[lr * ROW_FLOATS + lc * 3 + 1] * dom;
-                eb = raw[lr * ROW_FLOATS + lc * 3 + 2] * dom;
+                er = raw[lr * row_floats + lc * 3 + 0] * dom;
+                eg = raw[lr * row_floats + lc * 3 + 1] * dom;
+                eb = raw[lr * row_floats + lc * 3 + 2] * dom;
             }
             const float vd = rc.vhat[0] * dx + rc.vhat[1] * dy + rc.vhat[2] * dz;
             const float len2 = fmaxf(2.f + 2.f * vd, 1e-12f);
@@ -516,7 +516,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
             for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
 
 #pragma unroll 2
-        for (int t = u0; t < TILE_TEXELS; t += gk) {
+        for (int t = u0; t < tile_texels; t += gk) {
             const float4 h = rec[t * 3 + 0];
             const float4 s = rec[t * 3 + 1];
             float4 d4;
@@ -830,15 +830,18 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
 }
 
 struct RenderPlan {
-    int S, G, tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
+    int S, G, tt, tile_w, tile_h, tiles_x, tiles_y, ttiles_x, ttiles_y, splits;
 };
+
+// tile edge: tiles should span a few degrees so that the level schedule has something to decide on small maps
+static int tile_edge(int Hm) { return Hm >= 800 ? 32 : Hm >= 400 ? 16 : 8; }
 
 // slots per cell: S^2, raised to 16 for the 2x2 and 4x4 lattices so that their blocks are 8x8 cells (a tighter cone of
 // normals sends more tiles to the coarse levels) and to 4 for the 1x1 lattice (16x16-cell blocks cull a third of the
 // tiles that 32x32-cell blocks would visit)
 static int default_slots(int S) { return S == 1 ? 4 : (S == 2 || S == 4) ? 16 : S * S; }
 
-static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
+static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G, int tt) {
     RenderPlan p;
     p.S = S;
     p.G = G;
@@ -849,8 +852,9 @@ static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G) {
     p.tile_w = p.tile_h = e;
     p.tiles_x = (res + e - 1) / e;
     p.tiles_y = (res + e - 1) / e;
-    p.ttiles_x = (Wm + TT - 1) / TT;
-    p.ttiles_y = (Hm + TT - 1) / TT;
+    p.tt = tt;
+    p.ttiles_x = (Wm + tt - 1) / tt;
+    p.ttiles_y = (Hm + tt - 1) / tt;
     const long ctas = (long)p.tiles_x * p.tiles_y * N;
     // twelve waves of two resident CTAs per SM: a launch may serve only the fraction of the N renders routed to it (the
     // routing is decided on the device), so the grid is over-split to keep the GPU full and balanced in that case
@@ -891,11 +895,12 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.coarse_diffuse_ok = L.coarse_enabled && L.coarse_h <= 0.0135f;
     L.pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
     L.far_pair = (S == 8 || S == 16) && res >= FAR_EDGE;
-    L.raw = make_plan(N, He, We, res, S, default_slots(S));
-    L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE));
-    L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2));
-    L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S));
-    L.coarse2 = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S));
+    L.raw = make_plan(N, He, We, res, S, default_slots(S), tile_edge(He));
+    L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE), tile_edge(He));
+    // the coarse maps keep 32x32-cell tiles: their launches run few lattice levels and gain nothing from finer tiles
+    L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2), TT);
+    L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S), TT);
+    L.coarse2 = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), TT);
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -955,7 +960,7 @@ static void set_levels(GatherArgs& g, int S, bool hierarchy) {
     ++g.nlev;
 }
 
-static int make_tensor_map(CUtensorMap* tmap, const float* base, int B, int Hm, int Wm, int floats_per_cell) {
+static int make_tensor_map(CUtensorMap* tmap, const float* base, int B, int Hm, int Wm, int floats_per_cell, int tt) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) {
         set_error("render: cuTensorMapEncodeTiled entry point unavailable");
@@ -964,7 +969,7 @@ static int make_tensor_map(CUtensorMap* tmap, const float* base, int B, int Hm, 
     const cuuint64_t row = (cuuint64_t)Wm * floats_per_cell;
     cuuint64_t dims[3] = {row, (cuuint64_t)Hm, (cuuint64_t)B};
     cuuint64_t strides[2] = {row * 4, row * 4 * (cuuint64_t)Hm};
-    cuuint32_t box[3] = {(cuuint32_t)(TT * floats_per_cell), TT, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(tt * floats_per_cell), (cuuint32_t)tt, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1053,7 +1058,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     auto fill_plan = [&](GatherArgs& a, const RenderPlan& p) {
         a.tile_w = p.tile_w; a.tile_h = p.tile_h; a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y;
         a.ttiles_x = p.ttiles_x; a.ttiles_y = p.ttiles_y; a.splits = p.splits;
-        a.G = p.G;
+        a.G = p.G; a.tt = p.tt;
     };
     int rc_code;
     bool used_far = false, near_mode = false;
@@ -1067,7 +1072,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         a.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
-        if (a.use_tma && (rc_code = make_tensor_map(&tmap, env, B, He, We, 3)) != DRM_OK) return rc_code;
+        if (a.use_tma && (rc_code = make_tensor_map(&tmap, env, B, He, We, 3, L.raw.tt)) != DRM_OK) return rc_code;
         const bool pair = L.far_pair && hierarchy;
         const char* nv = getenv("DRM_RENDER_NEAR");  // "0": block/tile level schedule instead of the per-cell near kernel
         // measured (scripts/levels_probe.py): 2.4x / 1.6x faster than the block schedule for the 16x16 / 8x8 footprints,
@@ -1123,7 +1128,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         a.use_tma = ((L.Wc * COARSE_FLOATS * 4) % 16 == 0);
-        if (a.use_tma && (rc_code = make_tensor_map(&tmap, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS)) != DRM_OK) return rc_code;
+        if (a.use_tma && (rc_code = make_tensor_map(&tmap, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
         if (L.coarse_diffuse_ok) {
             a.slab = L.slab_diff; a.route_mask = ROUTE_DIFF_COARSE;
             fill_plan(a, L.diff);
@@ -1141,7 +1146,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         CUtensorMap tmap2;
         memset(&tmap2, 0, sizeof(tmap2));
         a2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
-        if (a2.use_tma && (rc_code = make_tensor_map(&tmap2, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS)) != DRM_OK) return rc_code;
+        if (a2.use_tma && (rc_code = make_tensor_map(&tmap2, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
         a2.slab = L.slab_coarse2; a2.route_mask = ROUTE_BOTH_COARSE2;
         fill_plan(a2, L.coarse2);
         set_levels(a2, S, hierarchy);
