@@ -62,3 +62,20 @@ def test_python_wrappers_refuse_cpu_tensors():
         refmap_mask_make(torch.ones(4, 3), torch.ones(4, 3), 16, 0.1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         render_batch(torch.ones(1, 8, 16, 3), torch.ones(1, 6), torch.ones(1, 3))
+
+
+def test_workspace_too_small_is_reported_before_any_device_work(lib):
+    """Pointers are never dereferenced on the host: a too-small workspace is refused with DRM_EWORKSPACE and a message
+    that states the size needed (no CUDA call has happened yet, so this runs without a GPU)."""
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    rc = lib.drm_render_refmaps(p, 1, 64, 128, None, p, p, None, 1, 16, 2, 0.0, 1, p, p, 64, None)
+    assert rc == _lib.DRM_EWORKSPACE
+    need = lib.drm_render_workspace_bytes(1, 1, 64, 128, 16, 2)
+    assert str(need).encode() in lib.drm_last_error()
+    with pytest.raises(_lib.DrmError):
+        _lib.check(rc)
+    rc = lib.drm_img2refmap(p, p, 0, p, 100, 1, 3, 16, 0.1, 0, 0, p, p, None, None, p, 64, None)
+    assert rc == _lib.DRM_EWORKSPACE
+    rc = lib.drm_render_refmaps(p, 1, 64, 128, None, p, p, None, 1, 16, 17, 0.0, 1, p, p, 64, None)
+    assert rc == _lib.DRM_EINVAL and b"footprint_S" in lib.drm_last_error()
