@@ -35,15 +35,16 @@ METRIC = "refmaps rendered/sec (128^2, 2000x1000 envmap)"
 
 
 def measured_traffic(batch, footprint):
-    """DRAM bytes of one step from the committed ncu capture (profiles/r1_traffic.json), for the workload it was taken on."""
+    """(DRAM bytes of one step, pipe utilisation of the gather kernel) from the committed ncu captures
+    (profiles/r1_traffic.json), for the workload they were taken on."""
     p = ROOT / "profiles" / "r1_traffic.json"
     try:
         d = json.loads(p.read_text())
         if d["workload"] == {"batch_per_gpu": batch, "footprint": footprint}:
-            return d["dram_bytes_per_step"]
+            return d["dram_bytes_per_step"], d.get("ncu_gather_pipes")
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def hbm_peak():
@@ -280,6 +281,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
+        traffic, pipes = measured_traffic(batch, args.footprint)
         # dominant kernel = render_gather_kernel: > 99 % of the step (see profiles/); achieved = algorithmic bytes of
         # the renders of this rank / event time of the step on the launching stream
         achieved = batch * ALG_BYTES_PER_REFMAP / (ms_per_step / 1e3) / 1e9
@@ -294,13 +296,14 @@ def main():
                        "l2": "inputs larger than L2 (1.5 GB of envmaps per GPU)", "parallelism": f"dp{world}",
                        "collective": "all_gather of rendered refmaps" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(batch, args.footprint), "algorithmic_bytes_per_step": batch * ALG_BYTES_PER_REFMAP,
+                         "traffic": traffic, "algorithmic_bytes_per_step": batch * ALG_BYTES_PER_REFMAP,
                          "peak_source": peak_src,
                          "note": "kernel is FP32/MUFU-pipe bound (FMA pipe 72% busy, DRAM 0.01%: profiles/), not HBM bound; "
                                  "see DESIGN.md 5"},
             "canonical_sum": {"pairs_per_step": pairs, "pairs_per_s_equivalent": pairs / (ms_per_step / 1e3),
                               "note": "(sub-normal, texel) terms of the defining sum; footprint levels and the coarse "
                                       "map evaluate far fewer"},
+            "ncu_gather_pipes": pipes,
             "e2e": {"value": e2e_value, "unit": "refmaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
