@@ -680,14 +680,16 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
     const int r_hi = whole ? g.He - 1 : min(g.He - 1, (int)ceilf((th_r + Rd) / dth));
     const float cosR = cosf(fminf(Rd, 3.14159265f)), sr = sinf(th_r), cr = cosf(th_r);
 
-    float4* mylist = lists + (size_t)warp * NEAR_LEVELS * NEAR_LIST * 2;
+    // staging lists of this warp, half vectors and radiances in separate arrays (16-byte stride: conflict-free LDS/STS)
+    float4* hlist = lists + (size_t)warp * NEAR_LEVELS * NEAR_LIST;
+    float4* elist = lists + (size_t)(NEAR_WARPS + warp) * NEAR_LEVELS * NEAR_LIST;
     int cnt[NEAR_LEVELS] = {0, 0, 0, 0};
     float tot0 = 0.f, tot1 = 0.f, tot2 = 0.f;
     const float* src = g.env + (size_t)rc.env * g.He * g.We * 3;
 
     auto process = [&](int l, int n) {  // lanes < n evaluate their staged texel against every node of lattice l
-        const float4 h = mylist[(l * NEAR_LIST + (lane < n ? lane : 0)) * 2 + 0];
-        const float4 es = mylist[(l * NEAR_LIST + (lane < n ? lane : 0)) * 2 + 1];
+        const float4 h = hlist[l * NEAR_LIST + (lane < n ? lane : 0)];
+        const float4 es = elist[l * NEAR_LIST + (lane < n ? lane : 0)];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         const int n0 = node_off[l], n1 = node_off[l + 1];
         for (int j = n0; j < n1; ++j) {
@@ -760,8 +762,8 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
                 if (!m) continue;
                 if (lvl == l) {
                     const int pos = cnt[l] + __popc(m & ((1u << lane) - 1u));
-                    mylist[(l * NEAR_LIST + pos) * 2 + 0] = h4;
-                    mylist[(l * NEAR_LIST + pos) * 2 + 1] = e4;
+                    hlist[l * NEAR_LIST + pos] = h4;
+                    elist[l * NEAR_LIST + pos] = e4;
                 }
                 cnt[l] += __popc(m);
                 __syncwarp();
@@ -771,13 +773,13 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
                     const int rest = cnt[l] - 32;
                     float4 t0, t1;
                     if (lane < rest) {
-                        t0 = mylist[(l * NEAR_LIST + 32 + lane) * 2 + 0];
-                        t1 = mylist[(l * NEAR_LIST + 32 + lane) * 2 + 1];
+                        t0 = hlist[l * NEAR_LIST + 32 + lane];
+                        t1 = elist[l * NEAR_LIST + 32 + lane];
                     }
                     __syncwarp();
                     if (lane < rest) {
-                        mylist[(l * NEAR_LIST + lane) * 2 + 0] = t0;
-                        mylist[(l * NEAR_LIST + lane) * 2 + 1] = t1;
+                        hlist[l * NEAR_LIST + lane] = t0;
+                        elist[l * NEAR_LIST + lane] = t1;
                     }
                     cnt[l] = rest;
                     __syncwarp();
