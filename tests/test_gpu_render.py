@@ -239,3 +239,29 @@ def test_hierarchy_partial_blocks_and_far_near_pair(res, S):
     ref = render_oracle(env, z, VIEWS[2], res, S=S, window=win)
     a, b = hier[win[0]:win[1], win[2]:win[3]], ref[win[0]:win[1], win[2]:win[3]]
     assert rel_l2(a, b) <= TOL
+
+
+def test_dropin_aovs_and_sensor_override():
+    """return_normal / return_depth outputs (utils/mitsuba3_utils.py:196-214) and the `sensor=` film-size override used by
+    DRMNet.instantiate_brdf_model (models/drmnet.py:331-343)."""
+    class Film:
+        def size(self):
+            return (24, 24)
+
+    class Sensor:  # stands in for the mitsuba sensor object: only its film size is consulted
+        def film(self):
+            return Film()
+
+    r = B200RefMapRenderer(refmap_res=16, envmap_size=(64, 128), return_normal=True, return_depth=True,
+                           brdf_param_names=BRDF_PARAM_NAMES, footprint_S=1)
+    env = torch.ones(64, 128, 3)  # a CPU tensor, as instantiate_brdf_model passes (the reference calls .cuda() on it)
+    img, normal, depth = r.rendering(torch.tensor(Z0), BRDF_PARAM_NAMES, envmap=env, channel_first=True)
+    assert img.shape == (3, 16, 16) and normal.shape == (3, 16, 16) and depth.shape == (1, 16, 16)
+    assert torch.allclose(normal.norm(dim=0), torch.ones(16, 16, device=DEV), atol=1e-6)
+    assert normal[2].min() > 0 and abs(float(normal[1, 0, 8]) - math.cos(0.5 * math.pi / 16)) < 1e-6  # row 0 faces +up
+    assert float(depth.min()) > 0.09 and float(depth.max()) < 1.1
+    big = r.rendering(torch.tensor(Z0), BRDF_PARAM_NAMES, sensor=Sensor())[0]
+    assert big.shape == (24, 24, 3)
+    assert (big[6:-6, 6:-6] - 1).abs().max() < 0.05  # white furnace, z0
+    big2 = r.rendering(torch.tensor(Z0), BRDF_PARAM_NAMES, sensor={"film": {"height": 20, "width": 20}})[0]
+    assert big2.shape == (20, 20, 3)
