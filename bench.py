@@ -118,9 +118,9 @@ def make_workload(batch: int, rank: int, device):
 
 
 def footprints(z, mode):
-    from drmnet_b200.renderer import auto_footprint
+    from drmnet_b200.renderer import auto_footprint, default_alpha_min
     if mode == "auto":
-        return [auto_footprint(float(r), RES) for r in z[:, 4].clip(0, 1)]
+        return [auto_footprint(float(r), RES, default_alpha_min(HE)) for r in z[:, 4].clip(0, 1)]
     return [int(mode)] * z.shape[0]
 
 
@@ -131,7 +131,7 @@ def cpu_port_sample(batch, n_renders, footprint):
     """The fp64 oracle port (C + OpenMP, all host cores) on a bounded sample of the workload: the first `n_renders`
     renders of rank 0's batch, each with its own footprint S, each on a k x k block of cells of the 128x128 refmap sized
     so one render costs about a second (cost ~ cells x S^2 x texels).  refmaps/s = sum(cell fractions) / sum(times)."""
-    from drmnet_b200.renderer import auto_footprint
+    from drmnet_b200.renderer import auto_footprint, default_alpha_min
     from drmnet_b200.synth import sample_brdf, sample_view, synthetic_envmap
     from oracle import render_oracle as ro
     ro.build()
@@ -143,7 +143,7 @@ def cpu_port_sample(batch, n_renders, footprint):
     frac_sum, t_sum, desc = 0.0, 0.0, []
     for b in range(n_renders):
         z = sample_brdf(1000 + b % batch)
-        S = auto_footprint(float(z[4]), RES) if footprint == "auto" else int(footprint)
+        S = auto_footprint(float(z[4]), RES, default_alpha_min(HE)) if footprint == "auto" else int(footprint)
         k = max(1, 24 // S)
         i0 = (RES - k) // 2
         t0 = time.perf_counter()

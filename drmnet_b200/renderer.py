@@ -15,6 +15,7 @@ models/drmnet.py:561-569 and :680-691.
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -36,11 +37,17 @@ def _slots(names: Sequence[str]) -> List[int]:
     return out
 
 
-def auto_footprint(roughness: float, res: int = 128) -> int:
+def default_alpha_min(He: int) -> float:
+    """Lower clamp of the GGX alpha the library applies when none is given: max(1e-3, 1.25 * pi / He)."""
+    return max(1e-3, 1.25 * math.pi / He)
+
+
+def auto_footprint(roughness: float, res: int = 128, alpha_min: float = 1e-3) -> int:
     """Gauss-Legendre points per axis (1, 2, 4, 8 or 16) that resolve the cell average of a GGX lobe of this roughness
-    to ~2e-4: the ratio of cell width to lobe half-width decides (measured with the fp64 oracle)."""
-    alpha = max(float(roughness) ** 2, 1e-3)
-    ratio = (torch.pi / res) / alpha
+    to ~2e-4: the ratio of cell width to lobe half-width decides (measured with the fp64 oracle).
+    ``alpha_min`` is the clamp the render will apply (``default_alpha_min(He)`` unless the caller overrides it)."""
+    alpha = max(float(roughness) ** 2, alpha_min)
+    ratio = (math.pi / res) / alpha
     if ratio < 0.1:
         return 1
     if ratio < 0.6:
@@ -102,7 +109,8 @@ def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor
     # grouped by S and each group is one launch
     if footprint_S is None:
         rough = z6[:, 4].clip(0, 1).tolist()  # one small device-to-host read
-        per_render = [auto_footprint(r, res) for r in rough]
+        amin = alpha_min if alpha_min and alpha_min > 0 else default_alpha_min(He)
+        per_render = [auto_footprint(r, res, amin) for r in rough]
     elif isinstance(footprint_S, int):
         per_render = None
     else:
@@ -235,7 +243,7 @@ class B200RefMapRenderer:
         res = self._film_res(sensor)
         S = self.footprint_S
         if S is None:
-            S = auto_footprint(float(z6[4].clip(0, 1)), res)
+            S = auto_footprint(float(z6[4].clip(0, 1)), res, self.alpha_min or default_alpha_min(env.shape[0]))
         img = render_batch(env[None], z6[None], view[None].to(self.device),
                            flip=torch.tensor([do_flip], device=self.device), res=res, footprint_S=S,
                            alpha_min=self.alpha_min or 0.0, channel_first=channel_first)[0]

@@ -22,7 +22,7 @@ for seed in (1004,):
     for rough, metal in ((0.0, 1.0), (0.08, 1.0), (0.11, 0.5), (0.15, 1.0), (0.18, 0.2), (0.22, 0.0), (0.3, 1.0), (0.4, 1.0)):
         z = torch.tensor([[metal, 0.9, 0.7, 0.5, rough, 0.8]])
         v = torch.tensor([[0.4, 0.0, 1.0]])
-        S = auto_footprint(rough, 128)
+        S = auto_footprint(rough, 128, 1.25 * 3.141592653589793 / 1000)
         ref, t0 = run(env, z, v, S, False)
         line = f"seed {seed} rough {rough:4.2f} metal {metal} S={S:2d} brute {t0*1e3:8.1f} ms |"
         for sc in scales:
