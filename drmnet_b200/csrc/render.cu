@@ -74,6 +74,10 @@ struct GatherArgs {
     int G;                     // sub-normal slots per refmap cell (a multiple of S*S)
     int part;                  // PART_ALL, or the far / near half of a launch pair (see far_tile)
     int far_edge;              // edge, in cells, of the blocks the far launch works on
+    int far_mode;              // 0: off; 1: raw-map launch skips tiles beyond dfar; 2: coarse-map launch keeps only those
+    float dfar;                // distance (block of cells to raw tile, half-vector space) beyond which the 2x2 map serves
+    int raw_tt, raw_ttiles_x, raw_Hm, raw_Wm;  // far_mode 2: geometry of the raw map's tiles (the unit of the decision)
+    float raw_dth, raw_dph;
     int nlev;                  // number of footprint levels used by this launch
     int lev_S[MAX_LEVELS];     // lattice size per axis of level k (ascending; the last one is S)
     int lev_tidx[MAX_LEVELS];  // log2(lev_S[k]): index into RenderConst::thr
@@ -249,12 +253,13 @@ __device__ __forceinline__ void cell_block_cone(const GatherArgs& g, const Rende
 // Distance, in half-vector space, between a cone of normals and the half vectors h = normalize(v + d) of one map tile;
 // -1 when no normal of the cone sees any direction of the tile (n.d <= 0 everywhere), -0.5 when the d -> h map is
 // singular over the tile (d ~ -v) and no bound is available.
-__device__ __forceinline__ float tile_distance(const GatherArgs& g, const float* __restrict__ vhat, int tile, float ax,
-                                               float ay, float az, float beta) {
-    const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
-    const int r0 = ty * g.tt, r1 = min(r0 + g.tt, g.Hm), c0 = tx * g.tt, c1 = min(c0 + g.tt, g.Wm);
-    const float dth = 0.5f * (r1 - r0) * g.dth_cell, dph = 0.5f * (c1 - c0) * g.dph_cell;
-    const float thc = fminf(0.5f * (r0 + r1) * g.dth_cell, 3.14159265f), phc = 0.5f * (c0 + c1) * g.dph_cell;
+__device__ __forceinline__ float tile_distance_geom(int cull, int tt, int ttiles_x, int Hm, int Wm, float dth_cell,
+                                                    float dph_cell, const float* __restrict__ vhat, int tile, float ax,
+                                                    float ay, float az, float beta) {
+    const int ty = tile / ttiles_x, tx = tile - ty * ttiles_x;
+    const int r0 = ty * tt, r1 = min(r0 + tt, Hm), c0 = tx * tt, c1 = min(c0 + tt, Wm);
+    const float dth = 0.5f * (r1 - r0) * dth_cell, dph = 0.5f * (c1 - c0) * dph_cell;
+    const float thc = fminf(0.5f * (r0 + r1) * dth_cell, 3.14159265f), phc = 0.5f * (c0 + c1) * dph_cell;
     float st, ct, sp, cp;
     sincosf(thc, &st, &ct);
     sincosf(phc, &sp, &cp);
@@ -262,7 +267,7 @@ __device__ __forceinline__ float tile_distance(const GatherArgs& g, const float*
     const float dps = dph * fminf(1.f, st + dth);
     const float gamma = (dth < 0.1f && dps < 0.1f) ? 1.05f * sqrtf(dth * dth + dps * dps) : dth + dps;
     const float dx = st * sp, dy = ct, dz = -st * cp;
-    if (g.cull) {
+    if (cull) {
         const float spread = beta + gamma + 0.01f;
         if (spread < 1.5607963f && ax * dx + ay * dy + az * dz <= -sinf(spread)) return -1.f;
     }
@@ -272,6 +277,11 @@ __device__ __forceinline__ float tile_distance(const GatherArgs& g, const float*
     const float gamma_h = gamma / (len - gamma);  // |dh| <= |dd| / |v + d|
     const float cosang = fminf(fmaxf((ax * hx + ay * hy + az * hz) / len, -1.f), 1.f);
     return fmaxf(acosf(cosang) - beta - gamma_h, 0.f);
+}
+
+__device__ __forceinline__ float tile_distance(const GatherArgs& g, const float* __restrict__ vhat, int tile, float ax,
+                                               float ay, float az, float beta) {
+    return tile_distance_geom(g.cull, g.tt, g.ttiles_x, g.Hm, g.Wm, g.dth_cell, g.dph_cell, vhat, tile, ax, ay, az, beta);
 }
 
 // Classify one map tile for the CTA whose cells are [pi0,pi1) x [pj0,pj1):
@@ -293,6 +303,7 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
     }
     const float dist = tile_distance(g, vhat, tile, ax, ay, az, beta);
     if (dist == -1.f) return 0;
+    if (g.far_mode == 1 && dist >= g.dfar) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
     if (g.nlev == 1) return 1;
     if (dist == -0.5f) return g.nlev;  // no bound: stay on the finest lattice
     for (int k = 0; k < g.nlev - 1; ++k)
@@ -473,6 +484,16 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 const float* cellp = raw + lr * row_floats + lc * COARSE_FLOATS;
                 dx = cellp[0]; dy = cellp[1]; dz = cellp[2];
                 er = cellp[3]; eg = cellp[4]; eb = cellp[5];
+                if (g.far_mode == 2) {
+                    // the raw tile this 2x2 cell lies in decides, with the function and inputs of the raw-map launch
+                    const int rr = (ty * tt + lr) * COARSE2, cc = (tx * tt + lc) * COARSE2;
+                    const int rtile = (rr / g.raw_tt) * g.raw_ttiles_x + cc / g.raw_tt;
+                    const bool inside = rr < g.raw_Hm && cc < g.raw_Wm;
+                    const float dr = inside ? tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth,
+                                                                 g.raw_dph, g.rc[k].vhat, rtile, ax, ay, az, beta)
+                                            : -1.f;
+                    if (!(dr >= g.dfar)) { er = 0.f; eg = 0.f; eb = 0.f; }
+                }
             } else {
                 const int r = min(ty * tt + lr, g.He - 1), c = min(tx * tt + lc, g.We - 1);
                 const float st = g.sin_t[r], ct = g.cos_t[r], sp = g.sin_p[c], cp = g.cos_p[c];
@@ -811,7 +832,7 @@ struct SlabDesc {
 };
 
 // out = sum over the launches that served the render and over their texel splits, in fixed order (deterministic)
-__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4, SlabDesc s5,
+__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4, SlabDesc s5, SlabDesc s6,
                                       const RenderConst* __restrict__ rc, float* __restrict__ out, int N, int res,
                                       int channel_first) {
     const size_t total = (size_t)N * res * res * 3;
@@ -822,9 +843,9 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
     const size_t k = o / 3 / ((size_t)res * res);
     const int route = rc[k].route;
     float v = 0.f;
-    const SlabDesc slabs[6] = {s0, s1, s2, s3, s4, s5};
+    const SlabDesc slabs[7] = {s0, s1, s2, s3, s4, s5, s6};
 #pragma unroll
-    for (int l = 0; l < 6; ++l)
+    for (int l = 0; l < 7; ++l)
         if (slabs[l].base && (route & slabs[l].route_mask))
             for (int s = 0; s < slabs[l].splits; ++s) v += slabs[l].base[(size_t)s * total + o];
     const size_t idx = channel_first ? (k * 3 + c) * res * res + pix : o;
@@ -880,10 +901,15 @@ struct RenderLayout {
     bool far_pair;  // the raw-map launch is split into a far launch (16x16-cell blocks) and a near launch
     bool pow2;      // S in {2,4,8,16}: the footprint hierarchy (and the per-cell near-field kernel) applies
     RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
+    RenderPlan mid, farc;  // near-mode far field: raw map within dfar / 2x2 coarse map beyond, both with 8x8-cell blocks
+    RenderPlan farc_raw;   // the same split for the block/tile schedule: coarse-map twin of `raw`
+    bool far_coarse_any;
+    bool far_coarse;       // the far field of sharp lobes beyond dfar is gathered from the 2x2 coarse map
+    float dfar;
     RenderConst* rc;
     int* env_used;
     float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_near, *slab_diff, *slab_coarse,
-        *slab_coarse2;
+        *slab_coarse2, *slab_farc;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -904,6 +930,17 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2), TT);
     L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S), TT);
     L.coarse2 = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), TT);
+    // Far field of sharp lobes (S >= 8) from the 2x2 coarse map: a tail ~ d^-4 evaluated once per cell of half-vector
+    // size h = coarse2_h / 2 is off by (h^2 / 24)(20 / d^2) locally; beyond dfar that is below 1e-4 even for a pixel
+    // whose value is all halo.
+    L.dfar = 0.5f * L.coarse2_h * sqrtf(20.f / (24.f * 1e-4f));
+    const char* fc = getenv("DRM_RENDER_FAR_COARSE");  // "0" disables (debugging / validation)
+    const char* lv0 = getenv("DRM_RENDER_LEVELS");  // "0": the single-level validation mode evaluates the full sum
+    L.far_coarse_any = L.coarse_enabled && L.dfar < 1.2f && !(fc && fc[0] == '0') && !(lv0 && lv0[0] == '0');
+    L.far_coarse = L.far_coarse_any && (S == 8 || S == 16);
+    L.farc_raw = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), TT);
+    L.mid = make_plan(N, He, We, res, 1, 16, tile_edge(He));
+    L.farc = make_plan(N, L.Hc2, L.Wc2, res, 1, 16, TT);
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -915,11 +952,12 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.coarse_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc * L.Wc * COARSE_FLOATS : 1);
     L.coarse2_map = c.take<float>(L.coarse_enabled ? (size_t)B * L.Hc2 * L.Wc2 * COARSE_FLOATS : 1);
     L.slab_raw = c.take<float>(slice * L.raw.splits);
-    L.slab_far = c.take<float>(L.pow2 ? slice * L.far.splits : 1);
+    L.slab_far = c.take<float>(L.pow2 ? slice * (L.far.splits > L.mid.splits ? L.far.splits : L.mid.splits) : 1);
     L.slab_near = c.take<float>(L.pow2 ? slice : 1);
     L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     L.slab_coarse2 = c.take<float>(L.coarse_enabled ? slice * L.coarse2.splits : 1);
+    L.slab_farc = c.take<float>(L.far_coarse_any ? slice * (L.farc.splits > L.farc_raw.splits ? L.farc.splits : L.farc_raw.splits) : 1);
     return c.used();
 }
 
@@ -1064,7 +1102,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         a.G = p.G; a.tt = p.tt;
     };
     int rc_code;
-    bool used_far = false, near_mode = false;
+    bool used_far = false, near_mode = false, used_farc = false;
     // ---- launches on the raw map: specular lobe only, and both lobes -------------------------------------------------
     {
         GatherArgs a = g;
@@ -1089,7 +1127,30 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         if (near_mode) {
             // specular-only renders: every (cell, texel) pair beyond the 1x1 threshold here, the rest per cell below
             f.part = PART_ALL; f.route_mask = ROUTE_SPEC_RAW;
-            if ((rc_code = launch_gather<1, false, true>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            used_farc = L.far_coarse;
+            if (used_farc) {
+                // ... and beyond dfar from the 2x2 coarse map: both launches use 8x8-cell blocks and take the decision
+                // per (block, raw tile) from the same function, so every pair is evaluated exactly once
+                fill_plan(f, L.mid);
+                f.far_mode = 1; f.dfar = L.dfar;
+                if ((rc_code = launch_gather<1, false, true>(f, tmap, L.mid, N, st)) != DRM_OK) return rc_code;
+                GatherArgs c2 = g;
+                c2.src = L.coarse2_map; c2.Hm = L.Hc2; c2.Wm = L.Wc2; c2.slab = L.slab_farc;
+                c2.dth_cell = (float)(COARSE2 * M_PI / He); c2.dph_cell = (float)(COARSE2 * 2.0 * M_PI / We);
+                fill_plan(c2, L.farc);
+                set_levels(c2, 1, false);
+                c2.part = PART_ALL; c2.route_mask = ROUTE_SPEC_RAW;
+                c2.far_mode = 2; c2.dfar = L.dfar;
+                c2.raw_tt = L.mid.tt; c2.raw_ttiles_x = L.mid.ttiles_x; c2.raw_Hm = He; c2.raw_Wm = We;
+                c2.raw_dth = a.dth_cell; c2.raw_dph = a.dph_cell;
+                CUtensorMap tmapc;
+                memset(&tmapc, 0, sizeof(tmapc));
+                c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
+                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
+                if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc, N, st)) != DRM_OK) return rc_code;
+            } else {
+                if ((rc_code = launch_gather<1, false, true>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            }
             NearArgs n{};
             n.env = env; n.rc = L.rc; n.sin_t = L.sin_t; n.cos_t = L.cos_t; n.sin_p = L.sin_p; n.cos_p = L.cos_p;
             n.slab = L.slab_near; n.He = He; n.We = We; n.N = N; n.res = res;
@@ -1106,10 +1167,32 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         } else {
             a.part = pair ? PART_NEAR : PART_ALL;
             a.route_mask = ROUTE_SPEC_RAW;
+            // same split for the block/tile schedule (any S): tiles beyond dfar come from the 2x2 coarse map, evaluated
+            // with the same blocks and lattices (a coarse tile is never farther than the raw tiles inside it, so its
+            // level is at least as fine)
+            used_farc = L.far_coarse_any && !pair;
+            if (used_farc) { a.far_mode = 1; a.dfar = L.dfar; }
             if ((rc_code = launch_gather<1, false>(a, tmap, L.raw, N, st)) != DRM_OK) return rc_code;
+            a.far_mode = 0;
             if (pair) {
                 f.part = PART_FAR; f.route_mask = ROUTE_SPEC_RAW;
                 if ((rc_code = launch_gather<1, false>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
+            }
+            if (used_farc) {
+                GatherArgs c2 = g;
+                c2.src = L.coarse2_map; c2.Hm = L.Hc2; c2.Wm = L.Wc2; c2.slab = L.slab_farc;
+                c2.dth_cell = (float)(COARSE2 * M_PI / He); c2.dph_cell = (float)(COARSE2 * 2.0 * M_PI / We);
+                fill_plan(c2, L.farc_raw);
+                set_levels(c2, S, hierarchy);
+                c2.part = PART_ALL; c2.route_mask = ROUTE_SPEC_RAW;
+                c2.far_mode = 2; c2.dfar = L.dfar;
+                c2.raw_tt = L.raw.tt; c2.raw_ttiles_x = L.raw.ttiles_x; c2.raw_Hm = He; c2.raw_Wm = We;
+                c2.raw_dth = a.dth_cell; c2.raw_dph = a.dph_cell;
+                CUtensorMap tmapc;
+                memset(&tmapc, 0, sizeof(tmapc));
+                c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
+                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
+                if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc_raw, N, st)) != DRM_OK) return rc_code;
             }
         }
         if (!L.coarse_diffuse_ok) {  // otherwise no render is routed to BOTH_RAW
@@ -1159,12 +1242,13 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         SlabDesc s0{L.slab_raw, L.raw.splits, (near_mode ? 0 : ROUTE_SPEC_RAW) | ROUTE_BOTH_RAW};
         SlabDesc s1{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff.splits, ROUTE_DIFF_COARSE};
         SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
-        SlabDesc s3{(used_far || near_mode) ? L.slab_far : nullptr, L.far.splits,
+        SlabDesc s3{(used_far || near_mode) ? L.slab_far : nullptr, used_farc ? L.mid.splits : L.far.splits,
                     ((used_far || near_mode) ? ROUTE_SPEC_RAW : 0) | (used_far ? ROUTE_BOTH_RAW : 0)};
         SlabDesc s5{near_mode ? L.slab_near : nullptr, 1, ROUTE_SPEC_RAW};
+        SlabDesc s6{used_farc ? L.slab_farc : nullptr, near_mode ? L.farc.splits : L.farc_raw.splits, ROUTE_SPEC_RAW};
         const size_t total = (size_t)N * res * res * 3;
         SlabDesc s4{L.coarse_enabled ? L.slab_coarse2 : nullptr, L.coarse2.splits, ROUTE_BOTH_COARSE2};
-        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, s5, L.rc, out, N, res, channel_first);
+        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, s5, s6, L.rc, out, N, res, channel_first);
         count_launches(1);
     }
     DRM_CHECK_CUDA(cudaGetLastError());
