@@ -304,6 +304,22 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
     const float dist = tile_distance(g, vhat, tile, ax, ay, az, beta);
     if (dist == -1.f) return 0;
     if (g.far_mode == 1 && dist >= g.dfar) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
+    if (g.far_mode == 2) {
+        // a coarse tile none of whose raw tiles is far for this block has nothing to contribute
+        const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
+        const int rt0 = (ty * g.tt * COARSE2) / g.raw_tt, ct0 = (tx * g.tt * COARSE2) / g.raw_tt;
+        const int nrt = (g.tt * COARSE2 + g.raw_tt - 1) / g.raw_tt;
+        const int raw_ttiles_y = (g.raw_Hm + g.raw_tt - 1) / g.raw_tt;
+        bool any_far = false;
+        for (int a = 0; a < nrt && !any_far; ++a)
+            for (int b = 0; b < nrt && !any_far; ++b) {
+                const int rt = rt0 + a, ct = ct0 + b;
+                if (rt >= raw_ttiles_y || ct >= g.raw_ttiles_x) continue;
+                any_far = tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth, g.raw_dph, vhat,
+                                             rt * g.raw_ttiles_x + ct, ax, ay, az, beta) >= g.dfar;
+            }
+        if (!any_far) return 0;
+    }
     if (g.nlev == 1) return 1;
     if (dist == -0.5f) return g.nlev;  // no bound: stay on the finest lattice
     for (int k = 0; k < g.nlev - 1; ++k)
