@@ -43,6 +43,7 @@ static constexpr int COARSE = 4;       // coarsening factor of the energy-centro
 static constexpr int COARSE2 = 2;      // finer coarsening for moderately rough specular lobes
 static constexpr int COARSE_FLOATS = 6;  // centroid direction + radiance * solid angle per coarse cell
 static constexpr int FAR_EDGE = 16;     // cells per side of the far launch's blocks
+static constexpr int FARC_TT = 16;      // tile edge (coarse cells) of the far-field launches on the 2x2 coarse map
 
 // A launch pair splits the (cell, tile) plane: the far launch takes, with large blocks of cells and the 1x1 lattice,
 // every tile that is far (1x1-accurate) from the whole block; the near launch takes the rest with small blocks.
@@ -950,13 +951,14 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     // size h = coarse2_h / 2 is off by (h^2 / 24)(20 / d^2) locally; beyond dfar that is below 1e-4 even for a pixel
     // whose value is all halo.
     L.dfar = 0.5f * L.coarse2_h * sqrtf(20.f / (24.f * 1e-4f));
+    if (const char* ds = getenv("DRM_RENDER_DFAR_SCALE")) L.dfar *= (float)atof(ds);
     const char* fc = getenv("DRM_RENDER_FAR_COARSE");  // "0" disables (debugging / validation)
     const char* lv0 = getenv("DRM_RENDER_LEVELS");  // "0": the single-level validation mode evaluates the full sum
     L.far_coarse_any = L.coarse_enabled && L.dfar < 1.2f && !(fc && fc[0] == '0') && !(lv0 && lv0[0] == '0');
     L.far_coarse = L.far_coarse_any && (S == 8 || S == 16);
-    L.farc_raw = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), TT);
+    L.farc_raw = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), FARC_TT);
     L.mid = make_plan(N, He, We, res, 1, 16, tile_edge(He));
-    L.farc = make_plan(N, L.Hc2, L.Wc2, res, 1, 16, TT);
+    L.farc = make_plan(N, L.Hc2, L.Wc2, res, 1, 16, FARC_TT);
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -1162,7 +1164,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 CUtensorMap tmapc;
                 memset(&tmapc, 0, sizeof(tmapc));
                 c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
-                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
+                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
                 if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc, N, st)) != DRM_OK) return rc_code;
             } else {
                 if ((rc_code = launch_gather<1, false, true>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
@@ -1207,7 +1209,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 CUtensorMap tmapc;
                 memset(&tmapc, 0, sizeof(tmapc));
                 c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
-                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
+                if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
                 if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc_raw, N, st)) != DRM_OK) return rc_code;
             }
         }
