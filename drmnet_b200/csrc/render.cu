@@ -84,6 +84,8 @@ struct GatherArgs {
     int lev_tidx[MAX_LEVELS];  // log2(lev_S[k]): index into RenderConst::thr
     float domega_k, cell, dth_cell, dph_cell;  // dth/dph: angular size of one map cell
     float gl_x[MAX_LEVELS][16], gl_w[MAX_LEVELS][16];
+    int fine_S;                // the render's own lattice (>= every lev_S) and its nodes: view_term_avg
+    float fine_x[16], fine_w[16];
 };
 
 __global__ void render_tables_kernel(float* sin_t, float* cos_t, float* sin_p, float* cos_p, int He, int We) {
@@ -159,6 +161,35 @@ __global__ void env_coarsen_kernel(const float* __restrict__ env, const float* _
     o[3] = M0; o[4] = M1; o[5] = M2;
 }
 
+// 16x16-texel cells from the 4x4 ones (only the lattice correction of the diffuse lobe reads them)
+__global__ void env_coarsen16_kernel(const float* __restrict__ coarse4, const int* __restrict__ used, int B, int Hc, int Wc,
+                                     int Hc16, int Wc16, float* __restrict__ coarse16) {
+    const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (cell >= (long)B * Hc16 * Wc16) return;
+    const int C = (int)(cell % Wc16), R = (int)((cell / Wc16) % Hc16), b = (int)(cell / ((long)Wc16 * Hc16));
+    if (!used[b]) return;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int dr = 0; dr < 4; ++dr) {
+        const int r = R * 4 + dr;
+        if (r >= Hc) break;
+        for (int dc = 0; dc < 4; ++dc) {
+            const int c = C * 4 + dc;
+            if (c >= Wc) break;
+            const float* e = coarse4 + (((size_t)b * Hc + r) * Wc + c) * COARSE_FLOATS;
+            const float w = e[3] + e[4] + e[5];
+            m0 += e[3]; m1 += e[4]; m2 += e[5];
+            cx += w * e[0]; cy += w * e[1]; cz += w * e[2];
+            gx += e[0]; gy += e[1]; gz += e[2];
+        }
+    }
+    float n2 = cx * cx + cy * cy + cz * cz;
+    if (!(n2 > 1e-30f)) { cx = gx; cy = gy; cz = gz; n2 = cx * cx + cy * cy + cz * cz; }
+    const float inv = rsqrtf(fmaxf(n2, 1e-38f));
+    float* o = coarse16 + (size_t)cell * COARSE_FLOATS;
+    o[0] = cx * inv; o[1] = cy * inv; o[2] = cz * inv;
+    o[3] = m0; o[4] = m1; o[5] = m2;
+}
+
 // clip z to [0,1] (mitsuba3_utils.py:239,242), derive the BSDF constants, the camera frame (:235-236), the footprint
 // level thresholds and the routing of the render's terms to the launches
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
@@ -223,6 +254,42 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
     int e = env_index ? env_index[k] : k;
     c.env = min(max(e, 0), B - 1);
     rc[k] = c;
+}
+
+// The view-side factor of the specular lobe, G1(n.v) / (4 n.v) D's normalisation included, depends on the normal only
+// and varies on the scale alpha at the limb (n.v -> 0), however far the texel is.  A node of a coarser lattice stands
+// for the m x m nodes of the render's own S x S lattice that lie in its sub-region (Gauss-Legendre nodes of order 2n
+// interlace the weight intervals of order n: m consecutive nodes per axis); it carries their weighted mean of this
+// factor, so the footprint levels approximate only the texel-dependent part.  m = 1 returns the factor itself.
+__device__ __forceinline__ float view_term(const RenderConst& rc, float lz) {
+    const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
+    return lz > 0.f ? 1.f / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+}
+
+// The node also moves by the shift of the region's centroid that this weighting causes (weighted minus unweighted
+// centroid of the fine nodes, in lattice coordinates): the first-order cross term between the view factor and the
+// texel-dependent part then cancels, and where the factor is flat the Gauss-Legendre node stays where it is.
+// fx(n), fw(n): node / weight n of the finest lattice (functors, so kernel parameters stay in the constant bank).
+// Returns {mean factor, shift along theta, shift along phi}.
+template <class FX, class FW>
+__device__ __forceinline__ float3 view_term_avg(const RenderConst& rc, float cell, int i, int j, int a, int b, int m,
+                                                FX fx, FW fw) {
+    float num = 0.f, den = 0.f, va = 0.f, vb = 0.f, ua = 0.f, ub = 0.f;
+    for (int ia = 0; ia < m; ++ia) {
+        const float xa = fx(a * m + ia), wa = fw(a * m + ia);
+        const float st = sinf(((float)i + 0.5f + 0.5f * xa) * cell);
+        for (int ib = 0; ib < m; ++ib) {
+            const float xb = fx(b * m + ib);
+            const float sp = sinf(((float)j + 0.5f + 0.5f * xb) * cell);
+            const float w = wa * fw(b * m + ib);
+            const float wv = w * view_term(rc, st * sp);
+            num += wv; den += w;
+            va += wv * xa; vb += wv * xb;
+            ua += w * xa; ub += w * xb;
+        }
+    }
+    if (!(num > 0.f)) return make_float3(0.f, 0.f, 0.f);
+    return make_float3(num / den, va / num - ua / den, vb / num - ub / den);
 }
 
 __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
@@ -457,8 +524,14 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 if (r == 0) u0 = sub - node * gk;
                 const int a = node / Sk, b = node - a * Sk;
                 const bool active = pl < npix && i < g.res && j < g.res;
-                const float th = ((float)i + 0.5f + 0.5f * g.gl_x[cur_level - 1][a]) * g.cell;
-                const float ph = ((float)j + 0.5f + 0.5f * g.gl_x[cur_level - 1][b]) * g.cell;
+                const bool avg = SPEC && g.fine_S > Sk && active;
+                float3 va = make_float3(0.f, 0.f, 0.f);
+                if (avg)
+                    va = view_term_avg(rc, g.cell, i, j, a, b, g.fine_S / Sk, [&](int n) { return g.fine_x[n]; },
+                                       [&](int n) { return g.fine_w[n]; });
+                if (DIFF) { va.y = 0.f; va.z = 0.f; }  // the diffuse lobe shares the node and has no such factor
+                const float th = ((float)i + 0.5f + 0.5f * (g.gl_x[cur_level - 1][a] + va.y)) * g.cell;
+                const float ph = ((float)j + 0.5f + 0.5f * (g.gl_x[cur_level - 1][b] + va.z)) * g.cell;
                 float st, ct, sp, cp;
                 sincosf(th, &st, &ct);
                 sincosf(ph, &sp, &cp);
@@ -473,6 +546,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 // F D G1(n.v) G1(n.d) / (4 n.v) = F x / (q^2 (x + sq)) / (pi alpha^2 (n.v + sqrt((n.v)^2 (1-a^2) + a^2)))
                 const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
                 mult[r] = lz > 0.f ? wq[r] / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+                if (avg) mult[r] = wq[r] * va.x;
             }
         }
         const int stage = it & 1;
@@ -650,6 +724,7 @@ struct NearArgs {
     const float *sin_t, *cos_t, *sin_p, *cos_p;
     float* slab;  // [N][res*res][3]
     int He, We, N, res, nlev;  // nlev lattices: 2, 4, ... 2^nlev
+    int view_avg;
     float domega_k, cell;
     float gl_x[NEAR_LEVELS][16], gl_w[NEAR_LEVELS][16];
 };
@@ -678,8 +753,13 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
         while (e >= node_off[l + 1]) ++l;
         const int Sk = 2 << l, node = e - node_off[l];
         const int a = node / Sk, b = node - a * Sk;
-        const float th = ((float)pi + 0.5f + 0.5f * g.gl_x[l][a]) * g.cell;
-        const float ph = ((float)pj + 0.5f + 0.5f * g.gl_x[l][b]) * g.cell;
+        const bool avg = g.view_avg && l < g.nlev - 1;
+        float3 va = make_float3(0.f, 0.f, 0.f);
+        if (avg)
+            va = view_term_avg(rc, g.cell, pi, pj, a, b, (2 << (g.nlev - 1)) / Sk,
+                               [&](int n) { return g.gl_x[g.nlev - 1][n]; }, [&](int n) { return g.gl_w[g.nlev - 1][n]; });
+        const float th = ((float)pi + 0.5f + 0.5f * (g.gl_x[l][a] + va.y)) * g.cell;
+        const float ph = ((float)pj + 0.5f + 0.5f * (g.gl_x[l][b] + va.z)) * g.cell;
         float st, ct, sp, cp;
         sincosf(th, &st, &ct);
         sincosf(ph, &sp, &cp);
@@ -689,11 +769,16 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
                                 lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2], lz);
         const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
         node_m[e] = lz > 0.f ? g.gl_w[l][a] * g.gl_w[l][b] / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+        if (avg) node_m[e] = g.gl_w[l][a] * g.gl_w[l][b] * va.x;
     }
-    // centre normal: the node of the tile kernel's 1x1 lattice, same expressions
+    // centre normal: the node of the tile kernel's 1x1 lattice (view-term shift included), same expressions
     float cnx, cny, cnz;
     {
-        const float th = ((float)pi + 0.5f + 0.5f * 0.f) * g.cell, ph = ((float)pj + 0.5f + 0.5f * 0.f) * g.cell;
+        float3 va = make_float3(0.f, 0.f, 0.f);
+        if (g.view_avg)
+            va = view_term_avg(rc, g.cell, pi, pj, 0, 0, 2 << (g.nlev - 1), [&](int n) { return g.gl_x[g.nlev - 1][n]; },
+                               [&](int n) { return g.gl_w[g.nlev - 1][n]; });
+        const float th = ((float)pi + 0.5f + 0.5f * (0.f + va.y)) * g.cell, ph = ((float)pj + 0.5f + 0.5f * (0.f + va.z)) * g.cell;
         float st, ct, sp, cp;
         sincosf(th, &st, &ct);
         sincosf(ph, &sp, &cp);
@@ -846,12 +931,17 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
 struct SlabDesc {
     const float* base;
     int splits, route_mask;
+    float sign;  // +1, or -1 for the centre-sample half of the diffuse lattice correction
+};
+
+static constexpr int MAX_SLABS = 9;
+struct SlabSet {
+    SlabDesc s[MAX_SLABS];
 };
 
 // out = sum over the launches that served the render and over their texel splits, in fixed order (deterministic)
-__global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, SlabDesc s3, SlabDesc s4, SlabDesc s5, SlabDesc s6,
-                                      const RenderConst* __restrict__ rc, float* __restrict__ out, int N, int res,
-                                      int channel_first) {
+__global__ void render_combine_kernel(const SlabSet set, const RenderConst* __restrict__ rc, float* __restrict__ out,
+                                      int N, int res, int channel_first) {
     const size_t total = (size_t)N * res * res * 3;
     size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (o >= total) return;
@@ -860,11 +950,10 @@ __global__ void render_combine_kernel(SlabDesc s0, SlabDesc s1, SlabDesc s2, Sla
     const size_t k = o / 3 / ((size_t)res * res);
     const int route = rc[k].route;
     float v = 0.f;
-    const SlabDesc slabs[7] = {s0, s1, s2, s3, s4, s5, s6};
 #pragma unroll
-    for (int l = 0; l < 7; ++l)
-        if (slabs[l].base && (route & slabs[l].route_mask))
-            for (int s = 0; s < slabs[l].splits; ++s) v += slabs[l].base[(size_t)s * total + o];
+    for (int l = 0; l < MAX_SLABS; ++l)
+        if (set.s[l].base && (route & set.s[l].route_mask))
+            for (int sp = 0; sp < set.s[l].splits; ++sp) v += set.s[l].sign * set.s[l].base[(size_t)sp * total + o];
     const size_t idx = channel_first ? (k * 3 + c) * res * res + pix : o;
     out[idx] = v;
 }
@@ -912,7 +1001,7 @@ static RenderPlan make_plan(int N, int Hm, int Wm, int res, int S, int G, int tt
 }
 
 struct RenderLayout {
-    int Hc, Wc, Hc2, Wc2;
+    int Hc, Wc, Hc2, Wc2, Hc16, Wc16;
     bool coarse_enabled, coarse_diffuse_ok;
     float coarse_h, coarse2_h;
     bool far_pair;  // the raw-map launch is split into a far launch (16x16-cell blocks) and a near launch
@@ -920,13 +1009,15 @@ struct RenderLayout {
     RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
     RenderPlan mid, farc;  // near-mode far field: raw map within dfar / 2x2 coarse map beyond, both with 8x8-cell blocks
     RenderPlan farc_raw;   // the same split for the block/tile schedule: coarse-map twin of `raw`
+    RenderPlan diff1, corr_hi, corr_lo;  // diffuse lobe: 1x1 lattice on the 4x4 map + (lattice - centre) on the 16x16 map
+    bool diff_corr;
     bool far_coarse_any;
     bool far_coarse;       // the far field of sharp lobes beyond dfar is gathered from the 2x2 coarse map
     float dfar;
     RenderConst* rc;
     int* env_used;
     float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_near, *slab_diff, *slab_coarse,
-        *slab_coarse2, *slab_farc;
+        *slab_coarse2, *slab_farc, *coarse16_map, *slab_corr_hi, *slab_corr_lo;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -934,6 +1025,8 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.Wc = (We + COARSE - 1) / COARSE;
     L.Hc2 = (He + COARSE2 - 1) / COARSE2;
     L.Wc2 = (We + COARSE2 - 1) / COARSE2;
+    L.Hc16 = (L.Hc + 3) / 4;
+    L.Wc16 = (L.Wc + 3) / 4;
     L.coarse_h = (float)(COARSE * M_PI / He);
     L.coarse2_h = (float)(COARSE2 * M_PI / He);
     const char* cv = getenv("DRM_RENDER_COARSE");  // "0" disables the coarse-map routes (debugging / validation)
@@ -945,6 +1038,13 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.far = make_plan(N, He, We, res, 1, SLOTS / (FAR_EDGE * FAR_EDGE), tile_edge(He));
     // the coarse maps keep 32x32-cell tiles: their launches run few lattice levels and gain nothing from finer tiles
     L.diff = make_plan(N, L.Hc, L.Wc, res, S < 2 ? S : 2, default_slots(S < 2 ? S : 2), TT);
+    // S >= 2: the cell average of the diffuse lobe differs from its centre sample by ~5e-5; that difference is smooth in
+    // the light direction, so it is taken from a 16x16-texel coarsening while the centre sample keeps the 4x4 map
+    const char* dc = getenv("DRM_RENDER_DIFF_CORR");  // "0" disables (debugging / validation)
+    L.diff_corr = L.coarse_diffuse_ok && S >= 2 && !(dc && dc[0] == '0');
+    L.diff1 = make_plan(N, L.Hc, L.Wc, res, 1, default_slots(1), TT);
+    L.corr_hi = make_plan(N, L.Hc16, L.Wc16, res, 2, default_slots(2), TT);
+    L.corr_lo = make_plan(N, L.Hc16, L.Wc16, res, 1, default_slots(1), TT);
     L.coarse = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S), TT);
     L.coarse2 = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), TT);
     // Far field of sharp lobes (S >= 8) from the 2x2 coarse map: a tail ~ d^-4 evaluated once per cell of half-vector
@@ -972,7 +1072,10 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.slab_raw = c.take<float>(slice * L.raw.splits);
     L.slab_far = c.take<float>(L.pow2 ? slice * (L.far.splits > L.mid.splits ? L.far.splits : L.mid.splits) : 1);
     L.slab_near = c.take<float>(L.pow2 ? slice : 1);
-    L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * L.diff.splits : 1);
+    L.slab_diff = c.take<float>(L.coarse_diffuse_ok ? slice * (L.diff.splits > L.diff1.splits ? L.diff.splits : L.diff1.splits) : 1);
+    L.coarse16_map = c.take<float>(L.diff_corr ? (size_t)B * L.Hc16 * L.Wc16 * COARSE_FLOATS : 1);
+    L.slab_corr_hi = c.take<float>(L.diff_corr ? slice * L.corr_hi.splits : 1);
+    L.slab_corr_lo = c.take<float>(L.diff_corr ? slice * L.corr_lo.splits : 1);
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     L.slab_coarse2 = c.take<float>(L.coarse_enabled ? slice * L.coarse2.splits : 1);
     L.slab_farc = c.take<float>(L.far_coarse_any ? slice * (L.farc.splits > L.farc_raw.splits ? L.farc.splits : L.farc_raw.splits) : 1);
@@ -1002,7 +1105,11 @@ static void gauss_legendre(int S, float* x, float* w) {
 
 // footprint levels of a launch: power-of-two lattices below S when S is one of 2,4,8,16 (S^2 then divides the 256
 // threads); any other S runs as a single level
-static void set_levels(GatherArgs& g, int S, bool hierarchy) {
+static void set_levels(GatherArgs& g, int S, bool hierarchy, int fine_S = 0) {
+    const char* va = getenv("DRM_RENDER_VIEW_AVG");  // "0": coarse lattice nodes carry their own view term (validation)
+    const bool fine_pow2 = (fine_S == 2 || fine_S == 4 || fine_S == 8 || fine_S == 16);
+    g.fine_S = (va && va[0] == '0') || !fine_pow2 ? 0 : fine_S;
+    if (g.fine_S) gauss_legendre(g.fine_S, g.fine_x, g.fine_w);
     g.S = S;
     g.nlev = 0;
     const bool pow2 = (S == 2 || S == 4 || S == 8 || S == 16);
@@ -1111,6 +1218,12 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         env_coarsen_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(env, L.sin_t, L.cos_t, L.sin_p, L.cos_p, L.env_used,
                                                                             B, He, We, L.Hc, L.Wc, L.Hc2, L.Wc2, g.domega_k,
                                                                             L.coarse_map, L.coarse2_map);
+        if (L.diff_corr) {
+            const long cells16 = (long)B * L.Hc16 * L.Wc16;
+            env_coarsen16_kernel<<<(unsigned)((cells16 + 255) / 256), 256, 0, st>>>(L.coarse_map, L.env_used, B, L.Hc, L.Wc,
+                                                                                L.Hc16, L.Wc16, L.coarse16_map);
+            count_launches(1);
+        }
         count_launches(2);
     }
 
@@ -1127,7 +1240,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         a.src = env; a.Hm = He; a.Wm = We; a.slab = L.slab_raw;
         a.dth_cell = (float)(M_PI / He); a.dph_cell = (float)(2.0 * M_PI / We);
         fill_plan(a, L.raw);
-        set_levels(a, S, hierarchy);
+        set_levels(a, S, hierarchy, S);
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         a.use_tma = ((We * 12) % 16 == 0) && ((reinterpret_cast<uintptr_t>(env) & 15) == 0);
@@ -1141,7 +1254,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         GatherArgs f = a;
         f.slab = L.slab_far;
         fill_plan(f, L.far);
-        set_levels(f, 1, false);
+        set_levels(f, 1, false, S);
         if (near_mode) {
             // specular-only renders: every (cell, texel) pair beyond the 1x1 threshold here, the rest per cell below
             f.part = PART_ALL; f.route_mask = ROUTE_SPEC_RAW;
@@ -1156,7 +1269,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 c2.src = L.coarse2_map; c2.Hm = L.Hc2; c2.Wm = L.Wc2; c2.slab = L.slab_farc;
                 c2.dth_cell = (float)(COARSE2 * M_PI / He); c2.dph_cell = (float)(COARSE2 * 2.0 * M_PI / We);
                 fill_plan(c2, L.farc);
-                set_levels(c2, 1, false);
+                set_levels(c2, 1, false, S);
                 c2.part = PART_ALL; c2.route_mask = ROUTE_SPEC_RAW;
                 c2.far_mode = 2; c2.dfar = L.dfar;
                 c2.raw_tt = L.mid.tt; c2.raw_ttiles_x = L.mid.ttiles_x; c2.raw_Hm = He; c2.raw_Wm = We;
@@ -1174,6 +1287,10 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
             n.slab = L.slab_near; n.He = He; n.We = We; n.N = N; n.res = res;
             n.domega_k = g.domega_k; n.cell = g.cell;
             n.nlev = 0;
+            {
+                const char* va = getenv("DRM_RENDER_VIEW_AVG");
+                n.view_avg = !(va && va[0] == '0');
+            }
             for (int sk = 2; sk <= S; sk *= 2) {
                 gauss_legendre(sk, n.gl_x[n.nlev], n.gl_w[n.nlev]);
                 ++n.nlev;
@@ -1201,7 +1318,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 c2.src = L.coarse2_map; c2.Hm = L.Hc2; c2.Wm = L.Wc2; c2.slab = L.slab_farc;
                 c2.dth_cell = (float)(COARSE2 * M_PI / He); c2.dph_cell = (float)(COARSE2 * 2.0 * M_PI / We);
                 fill_plan(c2, L.farc_raw);
-                set_levels(c2, S, hierarchy);
+                set_levels(c2, S, hierarchy, S);
                 c2.part = PART_ALL; c2.route_mask = ROUTE_SPEC_RAW;
                 c2.far_mode = 2; c2.dfar = L.dfar;
                 c2.raw_tt = L.raw.tt; c2.raw_ttiles_x = L.raw.ttiles_x; c2.raw_Hm = He; c2.raw_Wm = We;
@@ -1235,13 +1352,33 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         if (a.use_tma && (rc_code = make_tensor_map(&tmap, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
         if (L.coarse_diffuse_ok) {
             a.slab = L.slab_diff; a.route_mask = ROUTE_DIFF_COARSE;
-            fill_plan(a, L.diff);
-            set_levels(a, L.diff.S, false);
-            if ((rc_code = launch_gather<2, true>(a, tmap, L.diff, N, st)) != DRM_OK) return rc_code;
+            const RenderPlan& dp = L.diff_corr ? L.diff1 : L.diff;
+            fill_plan(a, dp);
+            set_levels(a, dp.S, false);
+            if ((rc_code = launch_gather<2, true>(a, tmap, dp, N, st)) != DRM_OK) return rc_code;
+            if (L.diff_corr) {
+                // + (2x2 lattice - centre sample) on the 16x16-texel map
+                GatherArgs c16 = g;
+                c16.src = L.coarse16_map; c16.Hm = L.Hc16; c16.Wm = L.Wc16;
+                c16.dth_cell = (float)(4 * COARSE * M_PI / He); c16.dph_cell = (float)(4 * COARSE * 2.0 * M_PI / We);
+                c16.route_mask = ROUTE_DIFF_COARSE;
+                CUtensorMap tmap16;
+                memset(&tmap16, 0, sizeof(tmap16));
+                c16.use_tma = ((L.Wc16 * COARSE_FLOATS * 4) % 16 == 0);
+                if (c16.use_tma && (rc_code = make_tensor_map(&tmap16, L.coarse16_map, B, L.Hc16, L.Wc16, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
+                c16.slab = L.slab_corr_hi;
+                fill_plan(c16, L.corr_hi);
+                set_levels(c16, 2, false);
+                if ((rc_code = launch_gather<2, true>(c16, tmap16, L.corr_hi, N, st)) != DRM_OK) return rc_code;
+                c16.slab = L.slab_corr_lo;
+                fill_plan(c16, L.corr_lo);
+                set_levels(c16, 1, false);
+                if ((rc_code = launch_gather<2, true>(c16, tmap16, L.corr_lo, N, st)) != DRM_OK) return rc_code;
+            }
         }
         a.slab = L.slab_coarse; a.route_mask = ROUTE_BOTH_COARSE;
         fill_plan(a, L.coarse);
-        set_levels(a, S, hierarchy);
+        set_levels(a, S, hierarchy, S);
         if ((rc_code = launch_gather<3, true>(a, tmap, L.coarse, N, st)) != DRM_OK) return rc_code;
         // the 2x2 coarsening: both lobes of the moderately rough renders
         GatherArgs a2 = g;
@@ -1253,20 +1390,25 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         if (a2.use_tma && (rc_code = make_tensor_map(&tmap2, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, TT)) != DRM_OK) return rc_code;
         a2.slab = L.slab_coarse2; a2.route_mask = ROUTE_BOTH_COARSE2;
         fill_plan(a2, L.coarse2);
-        set_levels(a2, S, hierarchy);
+        set_levels(a2, S, hierarchy, S);
         if ((rc_code = launch_gather<3, true>(a2, tmap2, L.coarse2, N, st)) != DRM_OK) return rc_code;
     }
     {
-        SlabDesc s0{L.slab_raw, L.raw.splits, (near_mode ? 0 : ROUTE_SPEC_RAW) | ROUTE_BOTH_RAW};
-        SlabDesc s1{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff.splits, ROUTE_DIFF_COARSE};
-        SlabDesc s2{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE};
-        SlabDesc s3{(used_far || near_mode) ? L.slab_far : nullptr, used_farc ? L.mid.splits : L.far.splits,
-                    ((used_far || near_mode) ? ROUTE_SPEC_RAW : 0) | (used_far ? ROUTE_BOTH_RAW : 0)};
-        SlabDesc s5{near_mode ? L.slab_near : nullptr, 1, ROUTE_SPEC_RAW};
-        SlabDesc s6{used_farc ? L.slab_farc : nullptr, near_mode ? L.farc.splits : L.farc_raw.splits, ROUTE_SPEC_RAW};
+        SlabSet set{};
+        set.s[0] = SlabDesc{L.slab_raw, L.raw.splits, (near_mode ? 0 : ROUTE_SPEC_RAW) | ROUTE_BOTH_RAW, 1.f};
+        set.s[1] = SlabDesc{L.coarse_diffuse_ok ? L.slab_diff : nullptr, L.diff_corr ? L.diff1.splits : L.diff.splits,
+                            ROUTE_DIFF_COARSE, 1.f};
+        set.s[2] = SlabDesc{L.coarse_enabled ? L.slab_coarse : nullptr, L.coarse.splits, ROUTE_BOTH_COARSE, 1.f};
+        set.s[3] = SlabDesc{(used_far || near_mode) ? L.slab_far : nullptr,
+                            (near_mode && used_farc) ? L.mid.splits : L.far.splits,
+                            ((used_far || near_mode) ? ROUTE_SPEC_RAW : 0) | (used_far ? ROUTE_BOTH_RAW : 0), 1.f};
+        set.s[4] = SlabDesc{L.coarse_enabled ? L.slab_coarse2 : nullptr, L.coarse2.splits, ROUTE_BOTH_COARSE2, 1.f};
+        set.s[5] = SlabDesc{near_mode ? L.slab_near : nullptr, 1, ROUTE_SPEC_RAW, 1.f};
+        set.s[6] = SlabDesc{used_farc ? L.slab_farc : nullptr, near_mode ? L.farc.splits : L.farc_raw.splits, ROUTE_SPEC_RAW, 1.f};
+        set.s[7] = SlabDesc{L.diff_corr ? L.slab_corr_hi : nullptr, L.corr_hi.splits, ROUTE_DIFF_COARSE, 1.f};
+        set.s[8] = SlabDesc{L.diff_corr ? L.slab_corr_lo : nullptr, L.corr_lo.splits, ROUTE_DIFF_COARSE, -1.f};
         const size_t total = (size_t)N * res * res * 3;
-        SlabDesc s4{L.coarse_enabled ? L.slab_coarse2 : nullptr, L.coarse2.splits, ROUTE_BOTH_COARSE2};
-        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s0, s1, s2, s3, s4, s5, s6, L.rc, out, N, res, channel_first);
+        render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(set, L.rc, out, N, res, channel_first);
         count_launches(1);
     }
     DRM_CHECK_CUDA(cudaGetLastError());
