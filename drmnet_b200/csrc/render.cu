@@ -58,6 +58,7 @@ struct RenderConst {  // per render
     float base[3], cdiff[3];
     float thr[MAX_LEVELS];  // half-vector-space distance beyond which footprint level k is accurate enough
     float tk2[MAX_LEVELS];  // the same for one cell: squared chord |n_centre - h|^2 thresholds (cell radius included)
+    float near_reach;       // angle of the chord tk2[0]: nothing closer may leave the raw map in near mode
     int env, route;
 };
 
@@ -77,6 +78,7 @@ struct GatherArgs {
     int far_edge;              // edge, in cells, of the blocks the far launch works on
     int far_mode;              // 0: off; 1: raw-map launch skips tiles beyond dfar; 2: coarse-map launch keeps only those
     float dfar;                // distance (block of cells to raw tile, half-vector space) beyond which the 2x2 map serves
+    int dfar_near;             // near mode: ... and never closer than the render's near_reach (render_near_kernel's pairs)
     int raw_tt, raw_ttiles_x, raw_Hm, raw_Wm;  // far_mode 2: geometry of the raw map's tiles (the unit of the decision)
     float raw_dth, raw_dph;
     int nlev;                  // number of footprint levels used by this launch
@@ -226,6 +228,7 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
             const float t = c.thr[i] * (near_scale / level_scale) + 0.75f * cell;  // nodes lie within 0.75 cell of the centre
             c.tk2[i] = i < MAX_LEVELS - 1 ? t * t : 0.f;
         }
+        c.near_reach = 2.f * asinf(fminf(1.f, 0.5f * sqrtf(c.tk2[0]))) + 2e-3f;
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     const bool has_diffuse = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
@@ -262,8 +265,8 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
 // interlace the weight intervals of order n: m consecutive nodes per axis); it carries their weighted mean of this
 // factor, so the footprint levels approximate only the texel-dependent part.  m = 1 returns the factor itself.
 __device__ __forceinline__ float view_term(const RenderConst& rc, float lz) {
-    const float g1 = lz + sqrtf(lz * lz * rc.one_m_a2 + rc.alpha2);
-    return lz > 0.f ? 1.f / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
+    const float g1 = lz + fast_sqrt(lz * lz * rc.one_m_a2 + rc.alpha2);
+    return lz > 0.f ? fast_rcp(3.14159265358979f * rc.alpha2 * g1) : 0.f;
 }
 
 // The node also moves by the shift of the region's centroid that this weighting causes (weighted minus unweighted
@@ -275,12 +278,14 @@ template <class FX, class FW>
 __device__ __forceinline__ float3 view_term_avg(const RenderConst& rc, float cell, int i, int j, int a, int b, int m,
                                                 FX fx, FW fw) {
     float num = 0.f, den = 0.f, va = 0.f, vb = 0.f, ua = 0.f, ub = 0.f;
+    float sps[16];
+    for (int ib = 0; ib < m; ++ib) sps[ib] = sinf(((float)j + 0.5f + 0.5f * fx(b * m + ib)) * cell);
     for (int ia = 0; ia < m; ++ia) {
         const float xa = fx(a * m + ia), wa = fw(a * m + ia);
         const float st = sinf(((float)i + 0.5f + 0.5f * xa) * cell);
         for (int ib = 0; ib < m; ++ib) {
             const float xb = fx(b * m + ib);
-            const float sp = sinf(((float)j + 0.5f + 0.5f * xb) * cell);
+            const float sp = sps[ib];
             const float w = wa * fw(b * m + ib);
             const float wv = w * view_term(rc, st * sp);
             num += wv; den += w;
@@ -290,6 +295,10 @@ __device__ __forceinline__ float3 view_term_avg(const RenderConst& rc, float cel
     }
     if (!(num > 0.f)) return make_float3(0.f, 0.f, 0.f);
     return make_float3(num / den, va / num - ua / den, vb / num - ub / den);
+}
+
+__device__ __forceinline__ float far_switch(const GatherArgs& g, const RenderConst& rc) {
+    return g.dfar_near ? fmaxf(g.dfar, rc.near_reach) : g.dfar;
 }
 
 __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
@@ -371,7 +380,7 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
     }
     const float dist = tile_distance(g, vhat, tile, ax, ay, az, beta);
     if (dist == -1.f) return 0;
-    if (g.far_mode == 1 && dist >= g.dfar) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
+    if (g.far_mode == 1 && dist >= far_switch(g, rcs)) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
     if (g.far_mode == 2) {
         // a coarse tile none of whose raw tiles is far for this block has nothing to contribute
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
@@ -384,7 +393,7 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
                 const int rt = rt0 + a, ct = ct0 + b;
                 if (rt >= raw_ttiles_y || ct >= g.raw_ttiles_x) continue;
                 any_far = tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth, g.raw_dph, vhat,
-                                             rt * g.raw_ttiles_x + ct, ax, ay, az, beta) >= g.dfar;
+                                             rt * g.raw_ttiles_x + ct, ax, ay, az, beta) >= far_switch(g, rcs);
             }
         if (!any_far) return 0;
     }
@@ -583,7 +592,7 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                     const float dr = inside ? tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth,
                                                                  g.raw_dph, g.rc[k].vhat, rtile, ax, ay, az, beta)
                                             : -1.f;
-                    if (!(dr >= g.dfar)) { er = 0.f; eg = 0.f; eb = 0.f; }
+                    if (!(dr >= far_switch(g, rc))) { er = 0.f; eg = 0.f; eb = 0.f; }
                 }
             } else {
                 const int r = min(ty * tt + lr, g.He - 1), c = min(tx * tt + lc, g.We - 1);
@@ -771,13 +780,37 @@ __global__ void __launch_bounds__(NEAR_THREADS) render_near_kernel(const NearArg
         node_m[e] = lz > 0.f ? g.gl_w[l][a] * g.gl_w[l][b] / (3.14159265358979f * rc.alpha2 * g1) : 0.f;
         if (avg) node_m[e] = g.gl_w[l][a] * g.gl_w[l][b] * va.x;
     }
-    // centre normal: the node of the tile kernel's 1x1 lattice (view-term shift included), same expressions
+    // centre normal: the node of the tile kernel's 1x1 lattice, view-term shift included (view_term_avg with m = S, one
+    // fine node per thread and a fixed-order reduction; it may differ from the tile kernel's value in the last bits,
+    // which moves a texel across the near / far boundary only if its distance equals the threshold to 1e-7)
     float cnx, cny, cnz;
     {
+        __shared__ float cred[NEAR_WARPS][6];
         float3 va = make_float3(0.f, 0.f, 0.f);
-        if (g.view_avg)
-            va = view_term_avg(rc, g.cell, pi, pj, 0, 0, 2 << (g.nlev - 1), [&](int n) { return g.gl_x[g.nlev - 1][n]; },
-                               [&](int n) { return g.gl_w[g.nlev - 1][n]; });
+        if (g.view_avg) {
+            const int m = 2 << (g.nlev - 1);
+            float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (tid < m * m) {
+                const int ia = tid / m, ib = tid - ia * m;
+                const float xa = g.gl_x[g.nlev - 1][ia], xb = g.gl_x[g.nlev - 1][ib];
+                const float w = g.gl_w[g.nlev - 1][ia] * g.gl_w[g.nlev - 1][ib];
+                const float wv = w * view_term(rc, sinf(((float)pi + 0.5f + 0.5f * xa) * g.cell) *
+                                                       sinf(((float)pj + 0.5f + 0.5f * xb) * g.cell));
+                p[0] = wv; p[1] = w; p[2] = wv * xa; p[3] = wv * xb; p[4] = w * xa; p[5] = w * xb;
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                for (int d = 16; d; d >>= 1) p[c] += __shfl_xor_sync(0xffffffffu, p[c], d);
+                if (lane == 0) cred[warp][c] = p[c];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                p[c] = 0.f;
+                for (int w = 0; w < NEAR_WARPS; ++w) p[c] += cred[w][c];
+            }
+            if (p[0] > 0.f) va = make_float3(p[0] / p[1], p[2] / p[0] - p[4] / p[1], p[3] / p[0] - p[5] / p[1]);
+        }
         const float th = ((float)pi + 0.5f + 0.5f * (0.f + va.y)) * g.cell, ph = ((float)pj + 0.5f + 0.5f * (0.f + va.z)) * g.cell;
         float st, ct, sp, cp;
         sincosf(th, &st, &ct);
@@ -1263,7 +1296,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 // ... and beyond dfar from the 2x2 coarse map: both launches use 8x8-cell blocks and take the decision
                 // per (block, raw tile) from the same function, so every pair is evaluated exactly once
                 fill_plan(f, L.mid);
-                f.far_mode = 1; f.dfar = L.dfar;
+                f.far_mode = 1; f.dfar = L.dfar; f.dfar_near = 1;
                 if ((rc_code = launch_gather<1, false, true>(f, tmap, L.mid, N, st)) != DRM_OK) return rc_code;
                 GatherArgs c2 = g;
                 c2.src = L.coarse2_map; c2.Hm = L.Hc2; c2.Wm = L.Wc2; c2.slab = L.slab_farc;
@@ -1271,7 +1304,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 fill_plan(c2, L.farc);
                 set_levels(c2, 1, false, S);
                 c2.part = PART_ALL; c2.route_mask = ROUTE_SPEC_RAW;
-                c2.far_mode = 2; c2.dfar = L.dfar;
+                c2.far_mode = 2; c2.dfar = L.dfar; c2.dfar_near = 1;
                 c2.raw_tt = L.mid.tt; c2.raw_ttiles_x = L.mid.ttiles_x; c2.raw_Hm = He; c2.raw_Wm = We;
                 c2.raw_dth = a.dth_cell; c2.raw_dph = a.dph_cell;
                 CUtensorMap tmapc;

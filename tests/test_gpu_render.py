@@ -241,6 +241,42 @@ def test_hierarchy_partial_blocks_and_far_near_pair(res, S):
     assert rel_l2(a, b) <= TOL
 
 
+# ---- regressions found by the seed sweeps of scripts/bisect_probe.py and scripts/scale_probe.py ---------------------
+def test_limb_cells_random_renders_full_size():
+    """Random sharp and glossy renders (the schedule's own footprints) on 2000x1000 maps: every accelerated stage against
+    the un-accelerated sum.  Before the coarse lattices carried the mean view term G1(n.v)/(4 n.v) of their sub-region
+    these were off by up to 3e-4, all of it in the limb rows / columns of the refmap."""
+    from drmnet_b200.synth import sample_brdf, sample_view
+    picks = [1, 5, 13, 21]
+    env = torch.stack([synthetic_envmap(1000, 2000, seed=100 + (i % 8), device=DEV) for i in picks])
+    z = torch.stack([sample_brdf(500 + i) for i in picks])
+    v = torch.stack([sample_view(500 + i) for i in picks])
+    idx = torch.arange(len(picks), dtype=torch.int32)
+    fast = render_batch(env, z, v, env_index=idx, res=128, footprint_S=None)
+    full = _with_env("DRM_RENDER_COARSE", "0", lambda: _with_levels(
+        "0", lambda: render_batch(env, z, v, env_index=idx, res=128, footprint_S=None)))
+    torch.cuda.synchronize()
+    for k in range(len(picks)):
+        e = rel_l2(fast[k].cpu().numpy(), full[k].cpu().numpy())
+        assert e <= 8e-5, (picks[k], e)
+    # the limb columns on their own (they carry < 1 % of the image norm)
+    a, b = fast[..., [0, 127]].cpu().numpy(), full[..., [0, 127]].cpu().numpy()
+    assert rel_l2(a, b) <= 2e-3
+
+
+@pytest.mark.parametrize("scale", ["2.0", "10.0"])
+def test_near_mode_far_coarse_partition_with_wide_near_field(scale):
+    """A near field (tk2[0]) wider than the distance at which the 2x2 map takes over: the raw-map and coarse-map far
+    launches must both yield to the per-cell kernel there (pairs were counted twice at the pole cell before)."""
+    env = synthetic_envmap(250, 500, seed=1004, device=DEV)[None]
+    z = torch.tensor([Z_CASES["z0_mirror"]])
+    v = torch.tensor([VIEWS[2]])
+    hier = _with_env("DRM_RENDER_LEVEL_SCALE", scale, lambda: render_batch(env, z, v, res=128, footprint_S=16))
+    flat = _with_levels("0", lambda: render_batch(env, z, v, res=128, footprint_S=16))
+    torch.cuda.synchronize()
+    assert rel_l2(hier.cpu().numpy(), flat.cpu().numpy()) <= 1e-5
+
+
 def test_dropin_aovs_and_sensor_override():
     """return_normal / return_depth outputs (utils/mitsuba3_utils.py:196-214) and the `sensor=` film-size override used by
     DRMNet.instantiate_brdf_model (models/drmnet.py:331-343)."""
