@@ -78,6 +78,8 @@ struct GatherArgs {
     int far_edge;              // edge, in cells, of the blocks the far launch works on
     int far_mode;              // 0: off; 1: raw-map launch skips tiles beyond dfar; 2: coarse-map launch keeps only those
     float dfar;                // distance (block of cells to raw tile, half-vector space) beyond which the 2x2 map serves
+    float dfar_hi;             // far_mode 2: ... and keeps only tiles closer than this (0: no upper end; the next coarser map)
+    int far_factor;            // far_mode 2: texels per cell edge of this launch's map (2 or 4)
     int dfar_near;             // near mode: ... and never closer than the render's near_reach (render_near_kernel's pairs)
     int raw_tt, raw_ttiles_x, raw_Hm, raw_Wm;  // far_mode 2: geometry of the raw map's tiles (the unit of the decision)
     float raw_dth, raw_dph;
@@ -297,8 +299,16 @@ __device__ __forceinline__ float3 view_term_avg(const RenderConst& rc, float cel
     return make_float3(num / den, va / num - ua / den, vb / num - ub / den);
 }
 
-__device__ __forceinline__ float far_switch(const GatherArgs& g, const RenderConst& rc) {
-    return g.dfar_near ? fmaxf(g.dfar, rc.near_reach) : g.dfar;
+// Distance (block of cells to raw tile, half-vector space) from which a coarsening whose base distance is D serves a
+// render: one evaluation per cell of half size h is off by ~ (h^2/24) 20 / (d^2 + 0.68 alpha^2), the tail's curvature
+// with the lobe's flat core folded in (at d = 0 this is the whole-map rule h <= 0.018 alpha of the routing).
+__device__ __forceinline__ float far_switch(const GatherArgs& g, const RenderConst& rc, float D) {
+    const float d = sqrtf(fmaxf(D * D - 0.676f * rc.alpha2, 0.f));
+    return g.dfar_near ? fmaxf(d, rc.near_reach) : d;
+}
+
+__device__ __forceinline__ bool far_in_range(const GatherArgs& g, const RenderConst& rc, float dr) {
+    return dr >= far_switch(g, rc, g.dfar) && (g.dfar_hi <= 0.f || dr < far_switch(g, rc, g.dfar_hi));
 }
 
 __device__ __forceinline__ float fresnel_dielectric(float cos_i, float eta) {
@@ -380,20 +390,20 @@ __device__ __forceinline__ int classify_tile(const GatherArgs& g, const RenderCo
     }
     const float dist = tile_distance(g, vhat, tile, ax, ay, az, beta);
     if (dist == -1.f) return 0;
-    if (g.far_mode == 1 && dist >= far_switch(g, rcs)) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
+    if (g.far_mode == 1 && dist >= far_switch(g, rcs, g.dfar)) return 0;  // served from the 2x2 coarse map by the far_mode 2 launch
     if (g.far_mode == 2) {
         // a coarse tile none of whose raw tiles is far for this block has nothing to contribute
         const int ty = tile / g.ttiles_x, tx = tile - ty * g.ttiles_x;
-        const int rt0 = (ty * g.tt * COARSE2) / g.raw_tt, ct0 = (tx * g.tt * COARSE2) / g.raw_tt;
-        const int nrt = (g.tt * COARSE2 + g.raw_tt - 1) / g.raw_tt;
+        const int rt0 = (ty * g.tt * g.far_factor) / g.raw_tt, ct0 = (tx * g.tt * g.far_factor) / g.raw_tt;
+        const int nrt = (g.tt * g.far_factor + g.raw_tt - 1) / g.raw_tt;
         const int raw_ttiles_y = (g.raw_Hm + g.raw_tt - 1) / g.raw_tt;
         bool any_far = false;
         for (int a = 0; a < nrt && !any_far; ++a)
             for (int b = 0; b < nrt && !any_far; ++b) {
                 const int rt = rt0 + a, ct = ct0 + b;
                 if (rt >= raw_ttiles_y || ct >= g.raw_ttiles_x) continue;
-                any_far = tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth, g.raw_dph, vhat,
-                                             rt * g.raw_ttiles_x + ct, ax, ay, az, beta) >= far_switch(g, rcs);
+                any_far = far_in_range(g, rcs, tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth,
+                                                                  g.raw_dph, vhat, rt * g.raw_ttiles_x + ct, ax, ay, az, beta));
             }
         if (!any_far) return 0;
     }
@@ -586,13 +596,13 @@ render_gather_kernel(const __grid_constant__ CUtensorMap tmap, const GatherArgs 
                 er = cellp[3]; eg = cellp[4]; eb = cellp[5];
                 if (g.far_mode == 2) {
                     // the raw tile this 2x2 cell lies in decides, with the function and inputs of the raw-map launch
-                    const int rr = (ty * tt + lr) * COARSE2, cc = (tx * tt + lc) * COARSE2;
+                    const int rr = (ty * tt + lr) * g.far_factor, cc = (tx * tt + lc) * g.far_factor;
                     const int rtile = (rr / g.raw_tt) * g.raw_ttiles_x + cc / g.raw_tt;
                     const bool inside = rr < g.raw_Hm && cc < g.raw_Wm;
                     const float dr = inside ? tile_distance_geom(g.cull, g.raw_tt, g.raw_ttiles_x, g.raw_Hm, g.raw_Wm, g.raw_dth,
                                                                  g.raw_dph, g.rc[k].vhat, rtile, ax, ay, az, beta)
                                             : -1.f;
-                    if (!(dr >= far_switch(g, rc))) { er = 0.f; eg = 0.f; eb = 0.f; }
+                    if (!far_in_range(g, rc, dr)) { er = 0.f; eg = 0.f; eb = 0.f; }
                 }
             } else {
                 const int r = min(ty * tt + lr, g.He - 1), c = min(tx * tt + lc, g.We - 1);
@@ -967,7 +977,7 @@ struct SlabDesc {
     float sign;  // +1, or -1 for the centre-sample half of the diffuse lattice correction
 };
 
-static constexpr int MAX_SLABS = 9;
+static constexpr int MAX_SLABS = 10;
 struct SlabSet {
     SlabDesc s[MAX_SLABS];
 };
@@ -1042,6 +1052,9 @@ struct RenderLayout {
     RenderPlan raw, far, diff, coarse, coarse2;  // launches: spec/both on the raw map (+ its far half), diffuse / both on the coarse maps
     RenderPlan mid, farc;  // near-mode far field: raw map within dfar / 2x2 coarse map beyond, both with 8x8-cell blocks
     RenderPlan farc_raw;   // the same split for the block/tile schedule: coarse-map twin of `raw`
+    RenderPlan farc4, farc4_raw;  // ... and beyond dfar4 the 4x4 coarse map
+    bool far_coarse4;
+    float dfar4;
     RenderPlan diff1, corr_hi, corr_lo;  // diffuse lobe: 1x1 lattice on the 4x4 map + (lattice - centre) on the 16x16 map
     bool diff_corr;
     bool far_coarse_any;
@@ -1050,7 +1063,7 @@ struct RenderLayout {
     RenderConst* rc;
     int* env_used;
     float *sin_t, *cos_t, *sin_p, *cos_p, *coarse_map, *coarse2_map, *slab_raw, *slab_far, *slab_near, *slab_diff, *slab_coarse,
-        *slab_coarse2, *slab_farc, *coarse16_map, *slab_corr_hi, *slab_corr_lo;
+        *slab_coarse2, *slab_farc, *slab_farc4, *coarse16_map, *slab_corr_hi, *slab_corr_lo;
 };
 
 static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -1092,6 +1105,12 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.farc_raw = make_plan(N, L.Hc2, L.Wc2, res, S, default_slots(S), FARC_TT);
     L.mid = make_plan(N, He, We, res, 1, 16, tile_edge(He));
     L.farc = make_plan(N, L.Hc2, L.Wc2, res, 1, 16, FARC_TT);
+    // twice as far the 4x4 map is as accurate as the 2x2 map at dfar
+    L.dfar4 = L.dfar * (float)(COARSE / COARSE2);
+    const char* f4 = getenv("DRM_RENDER_FAR_COARSE4");  // "0" disables (debugging / validation)
+    L.far_coarse4 = L.far_coarse_any && L.dfar4 < 1.4f && !(f4 && f4[0] == '0');
+    L.farc4_raw = make_plan(N, L.Hc, L.Wc, res, S, default_slots(S), FARC_TT);
+    L.farc4 = make_plan(N, L.Hc, L.Wc, res, 1, 16, FARC_TT);
     Carver c(ws);
     const size_t slice = (size_t)N * res * res * 3;
     L.rc = c.take<RenderConst>(N);
@@ -1112,6 +1131,7 @@ static size_t render_layout(RenderLayout& L, void* ws, int N, int B, int He, int
     L.slab_coarse = c.take<float>(L.coarse_enabled ? slice * L.coarse.splits : 1);
     L.slab_coarse2 = c.take<float>(L.coarse_enabled ? slice * L.coarse2.splits : 1);
     L.slab_farc = c.take<float>(L.far_coarse_any ? slice * (L.farc.splits > L.farc_raw.splits ? L.farc.splits : L.farc_raw.splits) : 1);
+    L.slab_farc4 = c.take<float>(L.far_coarse4 ? slice * (L.farc4.splits > L.farc4_raw.splits ? L.farc4.splits : L.farc4_raw.splits) : 1);
     return c.used();
 }
 
@@ -1311,7 +1331,20 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 memset(&tmapc, 0, sizeof(tmapc));
                 c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
                 if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
+                c2.far_factor = COARSE2; c2.dfar_hi = L.far_coarse4 ? L.dfar4 : 0.f;
                 if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc, N, st)) != DRM_OK) return rc_code;
+                if (L.far_coarse4) {
+                    GatherArgs c4 = c2;
+                    c4.src = L.coarse_map; c4.Hm = L.Hc; c4.Wm = L.Wc; c4.slab = L.slab_farc4;
+                    c4.dth_cell = (float)(COARSE * M_PI / He); c4.dph_cell = (float)(COARSE * 2.0 * M_PI / We);
+                    fill_plan(c4, L.farc4);
+                    c4.far_factor = COARSE; c4.dfar = L.dfar4; c4.dfar_hi = 0.f;
+                    CUtensorMap tmap4;
+                    memset(&tmap4, 0, sizeof(tmap4));
+                    c4.use_tma = ((L.Wc * COARSE_FLOATS * 4) % 16 == 0);
+                    if (c4.use_tma && (rc_code = make_tensor_map(&tmap4, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
+                    if ((rc_code = launch_gather<1, true>(c4, tmap4, L.farc4, N, st)) != DRM_OK) return rc_code;
+                }
             } else {
                 if ((rc_code = launch_gather<1, false, true>(f, tmap, L.far, N, st)) != DRM_OK) return rc_code;
             }
@@ -1360,7 +1393,20 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
                 memset(&tmapc, 0, sizeof(tmapc));
                 c2.use_tma = ((L.Wc2 * COARSE_FLOATS * 4) % 16 == 0);
                 if (c2.use_tma && (rc_code = make_tensor_map(&tmapc, L.coarse2_map, B, L.Hc2, L.Wc2, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
+                c2.far_factor = COARSE2; c2.dfar_hi = L.far_coarse4 ? L.dfar4 : 0.f;
                 if ((rc_code = launch_gather<1, true>(c2, tmapc, L.farc_raw, N, st)) != DRM_OK) return rc_code;
+                if (L.far_coarse4) {
+                    GatherArgs c4 = c2;
+                    c4.src = L.coarse_map; c4.Hm = L.Hc; c4.Wm = L.Wc; c4.slab = L.slab_farc4;
+                    c4.dth_cell = (float)(COARSE * M_PI / He); c4.dph_cell = (float)(COARSE * 2.0 * M_PI / We);
+                    fill_plan(c4, L.farc4_raw);
+                    c4.far_factor = COARSE; c4.dfar = L.dfar4; c4.dfar_hi = 0.f;
+                    CUtensorMap tmap4;
+                    memset(&tmap4, 0, sizeof(tmap4));
+                    c4.use_tma = ((L.Wc * COARSE_FLOATS * 4) % 16 == 0);
+                    if (c4.use_tma && (rc_code = make_tensor_map(&tmap4, L.coarse_map, B, L.Hc, L.Wc, COARSE_FLOATS, FARC_TT)) != DRM_OK) return rc_code;
+                    if ((rc_code = launch_gather<1, true>(c4, tmap4, L.farc4_raw, N, st)) != DRM_OK) return rc_code;
+                }
             }
         }
         if (!L.coarse_diffuse_ok) {  // otherwise no render is routed to BOTH_RAW
@@ -1440,6 +1486,8 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
         set.s[6] = SlabDesc{used_farc ? L.slab_farc : nullptr, near_mode ? L.farc.splits : L.farc_raw.splits, ROUTE_SPEC_RAW, 1.f};
         set.s[7] = SlabDesc{L.diff_corr ? L.slab_corr_hi : nullptr, L.corr_hi.splits, ROUTE_DIFF_COARSE, 1.f};
         set.s[8] = SlabDesc{L.diff_corr ? L.slab_corr_lo : nullptr, L.corr_lo.splits, ROUTE_DIFF_COARSE, -1.f};
+        set.s[9] = SlabDesc{(used_farc && L.far_coarse4) ? L.slab_farc4 : nullptr, near_mode ? L.farc4.splits : L.farc4_raw.splits,
+                            ROUTE_SPEC_RAW, 1.f};
         const size_t total = (size_t)N * res * res * 3;
         render_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(set, L.rc, out, N, res, channel_first);
         count_launches(1);

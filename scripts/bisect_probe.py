@@ -5,7 +5,7 @@ import torch
 from drmnet_b200 import synth
 from drmnet_b200.renderer import render_batch, auto_footprint
 
-SW = ["DRM_RENDER_COARSE", "DRM_RENDER_LEVELS", "DRM_RENDER_NEAR", "DRM_RENDER_FAR_COARSE", "DRM_RENDER_DIFF_CORR", "DRM_RENDER_VIEW_AVG"]
+SW = ["DRM_RENDER_COARSE", "DRM_RENDER_LEVELS", "DRM_RENDER_NEAR", "DRM_RENDER_FAR_COARSE", "DRM_RENDER_DIFF_CORR", "DRM_RENDER_VIEW_AVG", "DRM_RENDER_FAR_COARSE4"]
 
 def rel(a, b):
     return (torch.linalg.norm((a - b).flatten(1), dim=1) / torch.linalg.norm(b.flatten(1), dim=1))
