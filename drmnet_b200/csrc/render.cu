@@ -199,7 +199,7 @@ __global__ void env_coarsen16_kernel(const float* __restrict__ coarse4, const in
 __global__ void render_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                     const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N,
                                     int B, float alpha_min, float cell, float level_scale, float near_scale,
-                                    float coarse_h, float coarse2_h, int coarse_diffuse_ok,
+                                    float coarse_h, float coarse2_h, int coarse_diffuse_ok, int unify_coarse2,
                                     RenderConst* __restrict__ rc) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
@@ -240,7 +240,9 @@ __global__ void render_setup_kernel(const float* __restrict__ z6, const float* _
     const bool spec_coarse = coarse_h > 0.f && coarse_h <= 0.018f * alpha;
     const bool spec_coarse2 = coarse2_h > 0.f && coarse2_h <= 0.018f * alpha;
     if (spec_coarse) c.route = ROUTE_BOTH_COARSE;
-    else if (spec_coarse2) c.route = ROUTE_BOTH_COARSE2;
+    // (with the distance-switched far launches the 2x2 rule is their d = 0 case: such a render takes the raw-map
+    // route, whose raw launch then finds no tile, with the 4x4 map beyond its switch distance and for the diffuse lobe)
+    else if (spec_coarse2 && !unify_coarse2) c.route = ROUTE_BOTH_COARSE2;
     else if (!has_diffuse) c.route = ROUTE_SPEC_RAW;
     else c.route = coarse_diffuse_ok ? (ROUTE_SPEC_RAW | ROUTE_DIFF_COARSE) : ROUTE_BOTH_RAW;
     float vx = view3[3 * k], vy = view3[3 * k + 1], vz = view3[3 * k + 2];
@@ -1255,6 +1257,10 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
     g.cell = (float)(M_PI / res);
 
+    const char* nvs = getenv("DRM_RENDER_NEAR");
+    const char* un = getenv("DRM_RENDER_UNIFY");  // "0": moderately rough renders keep the both-lobes 2x2 launch (validation)
+    const bool unify = L.far_coarse4 && L.coarse_diffuse_ok && hierarchy && !(un && un[0] == '0') &&
+                       (!L.far_pair || !(nvs && nvs[0] == '0'));
     const int tb = 128;
     render_tables_kernel<<<(max(He, We) + tb - 1) / tb, tb, 0, st>>>(L.sin_t, L.cos_t, L.sin_p, L.cos_p, He, We);
     float near_scale = 2.f * level_scale;
@@ -1262,7 +1268,7 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
     render_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell, level_scale, near_scale,
                                                          L.coarse_enabled ? L.coarse_h : 0.f,
                                                          L.coarse_enabled ? L.coarse2_h : 0.f, L.coarse_diffuse_ok ? 1 : 0,
-                                                         L.rc);
+                                                         unify ? 1 : 0, L.rc);
     count_launches(2);
     if (L.coarse_enabled) {
         DRM_CHECK_CUDA(cudaMemsetAsync(L.env_used, 0, sizeof(int) * B, st));

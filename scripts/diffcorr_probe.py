@@ -26,7 +26,7 @@ def main():
     os.environ["DRM_RENDER_DIFF_CORR"] = "0"
     run()
     off, t_off = run()
-    for k in ("DRM_RENDER_COARSE", "DRM_RENDER_LEVELS", "DRM_RENDER_NEAR", "DRM_RENDER_FAR_COARSE", "DRM_RENDER_FAR_COARSE4"):
+    for k in ("DRM_RENDER_COARSE", "DRM_RENDER_LEVELS", "DRM_RENDER_NEAR", "DRM_RENDER_FAR_COARSE", "DRM_RENDER_FAR_COARSE4", "DRM_RENDER_UNIFY"):
         os.environ[k] = "0"
     full, _ = run()
     print("t_on %.3f t_off %.3f" % (t_on, t_off))
