@@ -298,7 +298,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_step": batch * ALG_BYTES_PER_REFMAP,
                          "peak_source": peak_src,
-                         "note": "kernel is FP32/MUFU-pipe bound (FMA pipe 72% busy, DRAM 0.01%: profiles/), not HBM bound; "
+                         "note": "kernel is FP32/MUFU-pipe bound (FMA pipe 60-71% busy, MUFU 48-56%, DRAM < 0.2%: profiles/r1_render_ncu_full_S*.csv), not HBM bound; "
                                  "see DESIGN.md 5"},
             "canonical_sum": {"pairs_per_step": pairs, "pairs_per_s_equivalent": pairs / (ms_per_step / 1e3),
                               "note": "(sub-normal, texel) terms of the defining sum; footprint levels and the coarse "
