@@ -12,10 +12,13 @@ def main():
     dev = "cuda:0"
     He, We = 1000, 2000
     B = 8
-    env = torch.stack([synth.synthetic_envmap(He, We, 100 + i, device=dev) for i in range(B)])
-    z = torch.stack([synth.sample_brdf(500 + i) for i in range(B * 3)]).to(dev)
-    view = torch.stack([synth.sample_view(500 + i) for i in range(B * 3)]).to(dev)
-    idx = (torch.arange(B * 3, device=dev) % B).int()
+    e0 = int(sys.argv[1]) if len(sys.argv) > 1 else 100   # envmap seed offset
+    z0 = int(sys.argv[2]) if len(sys.argv) > 2 else 500   # BRDF / view seed offset
+    R = int(sys.argv[3]) if len(sys.argv) > 3 else B * 3  # renders
+    env = torch.stack([synth.synthetic_envmap(He, We, e0 + i, device=dev) for i in range(B)])
+    z = torch.stack([synth.sample_brdf(z0 + i) for i in range(R)]).to(dev)
+    view = torch.stack([synth.sample_view(z0 + i) for i in range(R)]).to(dev)
+    idx = (torch.arange(R, device=dev) % B).int()
     def run():
         torch.cuda.synchronize(); t = time.time()
         o = render_batch(env, z, view, env_index=idx, res=128, footprint_S=None)
@@ -33,7 +36,7 @@ def main():
     r1, r2, r3 = rel(on, off), rel(on, full), rel(off, full)
     print("on vs off  max %.3e" % r1.max().item())
     print("on vs full max %.3e  off vs full max %.3e" % (r2.max().item(), r3.max().item()))
-    for i in range(B * 3):
+    for i in range(R):
         print(i, "r=%.3f m=%.2f" % (z[i, 4].item(), z[i, 0].item()), "%.2e %.2e %.2e" % (r1[i].item(), r2[i].item(), r3[i].item()))
 
 if __name__ == "__main__":
