@@ -2,7 +2,8 @@
 render_near_kernel, each band evaluated on its own lattice (with the view-term mean and centroid shift of
 view_term_avg: mode "shift"; mean only: "avg"; neither: "plain") against the full 16x16 lattice.
 
-usage: limb_levels_study.py ALPHA [shift|avg|plain]      (500x1000 synthetic map, res 128; minutes on one core)
+usage: limb_levels_study.py ALPHA [shift|avg|plain] [THRESHOLD_FACTOR] [limb] [MIN_LATTICE]   (500x1000 synthetic map, res 128;
+       minutes on one core; "limb": only the last four columns of row 64)
 """
 import math, sys, numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
@@ -30,8 +31,10 @@ def T(n, mask):
 ls, ns = 0.3, 0.6
 thr = [21 * math.sqrt(c * alpha), 7.5 * c ** (2 / 3) * alpha ** (1 / 3), 2.4 * c ** 0.8 * alpha ** 0.2, 1.2 * c ** (8 / 9) * alpha ** (1 / 9)]
 thr = [ls * max(x, 6 * alpha) for x in thr]
-tk = [x * (ns / ls) + 0.75 * c for x in thr] + [0.0]
+fac = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+tk = [fac * x * (ns / ls) + 0.75 * c for x in thr] + [0.0]
 xf, wf = GL[S]
+MINLAT = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 def node(i, j, Sk, a, b):
     m = S // Sk
     xs, ws = GL[Sk]
@@ -46,7 +49,8 @@ def node(i, j, Sk, a, b):
             num += wv; den += w; va += wv * xa; vb += wv * xb; ua += w * xa; ub += w * xb
     sa, sb = (va / num - ua / den, vb / num - ub / den) if mode == "shift" else (0.0, 0.0)
     return nrm((i + .5 + .5 * (xs[a] + sa)) * c, (j + .5 + .5 * (xs[b] + sb)) * c), ws[a] * ws[b] * num / den
-for (i, j) in ((64, 126), (64, 127), (63, 125), (64, 64), (20, 100)):
+CELLS = ((64, 127), (64, 126), (64, 125), (64, 124)) if len(sys.argv) > 4 else ((64, 126), (64, 127), (63, 125), (64, 64), (20, 100))
+for (i, j) in CELLS:
     n1, _ = node(i, j, 1, 0, 0)
     chord = np.linalg.norm(h - n1[None], axis=1)
     vis = ln > 0.05
@@ -64,6 +68,7 @@ for (i, j) in ((64, 126), (64, 127), (63, 125), (64, 64), (20, 100)):
                 if bands[k].any(): ex[k] += wv * T(n, bands[k])
     for k, Sk in enumerate((1, 2, 4, 8, 16)):
         if not bands[k].any(): continue
+        Sk = max(Sk, MINLAT)
         for a in range(Sk):
             for b in range(Sk):
                 n, wv = node(i, j, Sk, a, b)
