@@ -116,3 +116,19 @@ def test_envmap_directions_convention():
     assert d[0, :, 1].min() > 0 and d[-1, :, 1].max() < 0           # row 0 looks up (+Y)
     assert d[1, 0, 2] < 0 and d[1, 0, 0] > 0                         # column 0: just right of -Z
     assert d[1, 3, 2] > 0 or d[1, 4, 2] > 0                          # half way round: +Z
+
+
+def test_gauss_legendre_nodes_nest_in_the_weight_intervals_of_coarser_orders():
+    """What view_term_avg (render.cu) relies on: the m = S/Sk consecutive nodes a*m .. a*m+m-1 of the S-point rule lie
+    in the a-th weight interval of the Sk-point rule, for every footprint pair the level schedule uses."""
+    for S in (2, 4, 8, 16):
+        xf, _ = np.polynomial.legendre.leggauss(S)
+        Sk = S // 2
+        while Sk >= 1:
+            _, ws = np.polynomial.legendre.leggauss(Sk)
+            edges = np.concatenate([[-1.0], -1.0 + np.cumsum(ws)])
+            m = S // Sk
+            for a in range(Sk):
+                for i in range(m):
+                    assert edges[a] < xf[a * m + i] < edges[a + 1], (S, Sk, a, i)
+            Sk //= 2
