@@ -13,6 +13,21 @@ _lib = None
 DRM_OK, DRM_EINVAL, DRM_EWORKSPACE, DRM_ECUDA, DRM_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
+class RenderOptions(ctypes.Structure):
+    """DrmRenderOptions of include/drmrender.h: accuracy / cost constants of the hierarchical render."""
+    _fields_ = [("kappa", ctypes.c_float), ("rcap", ctypes.c_float), ("horizon", ctypes.c_float),
+                ("kappa_diffuse", ctypes.c_float), ("horizon_diffuse", ctypes.c_float),
+                ("level_scale", ctypes.c_float), ("level_scale0", ctypes.c_float),
+                ("pixel_covariance", ctypes.c_int), ("full_second_order", ctypes.c_int), ("alpha_full2", ctypes.c_float), ("hand_over", ctypes.c_float), ("limb_nv", ctypes.c_float),
+                ("limb_boost", ctypes.c_float), ("limb_x", ctypes.c_float)]
+
+
+def default_render_options() -> "RenderOptions":
+    o = RenderOptions()
+    lib().drm_render_default_options(ctypes.byref(o))
+    return o
+
+
 class DrmError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libdrmrender error {code}: {message}")
@@ -45,6 +60,17 @@ def lib() -> ctypes.CDLL:
     L.drm_render_workspace_bytes.argtypes = [i32] * 6
     L.drm_render_refmaps.restype = i32
     L.drm_render_refmaps.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, sz, vp]
+    L.drm_render_refmaps_opts.restype = i32
+    L.drm_render_refmaps_opts.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, sz, vp,
+                                          ctypes.POINTER(RenderOptions)]
+    L.drm_render_default_options.restype = None
+    L.drm_render_default_options.argtypes = [ctypes.POINTER(RenderOptions)]
+    L.drm_render_status.restype = i32
+    L.drm_render_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 16), vp]
+    L.drm_render_flat_workspace_bytes.restype = sz
+    L.drm_render_flat_workspace_bytes.argtypes = [i32] * 6
+    L.drm_render_refmaps_flat.restype = i32
+    L.drm_render_refmaps_flat.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, sz, vp]
     L.drm_img2refmap_workspace_bytes.restype = sz
     L.drm_img2refmap_workspace_bytes.argtypes = [i64, i32, i32, f32]
     L.drm_img2refmap.restype = i32
@@ -72,5 +98,7 @@ def check(code: int) -> None:
 
 
 EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_launch_count", "drm_render_workspace_bytes", "drm_render_refmaps",
+                    "drm_render_refmaps_opts", "drm_render_default_options", "drm_render_status",
+                    "drm_render_flat_workspace_bytes", "drm_render_refmaps_flat",
                     "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_normals_to_thetaphi",
                     "drm_refmap_postprocess", "drm_mirmap2envmap", "drm_refmap_lookup", "drm_normalized_log"]

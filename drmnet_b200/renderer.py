@@ -62,10 +62,15 @@ def auto_footprint(roughness: float, res: int = 128, alpha_min: float = 1e-3) ->
 def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor, *,
                  env_index: Optional[torch.Tensor] = None, flip: Optional[torch.Tensor] = None,
                  brdf_param_names: Optional[Sequence[str]] = None, res: int = 128, footprint_S=1,
-                 alpha_min: float = 0.0, channel_first: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 alpha_min: float = 0.0, channel_first: bool = True, out: Optional[torch.Tensor] = None,
+                 options=None, flat: bool = False, check_status: bool = False) -> torch.Tensor:
     """N renders in one launch.  envmaps [B,He,We,3] fp32 CUDA; z [N,P]; view_from [N,3]; env_index [N] int (default
-    arange, needs N == B); flip [N] bool; footprint_S an int, one int per render, or None (chosen per render from its
-    roughness by ``auto_footprint``).  Returns [N,3,res,res] (or [N,res,res,3])."""
+    arange, needs N == B); flip [N] bool; footprint_S 1, 2, 4, 8 or 16: an int, one per render, or None (chosen per
+    render from its roughness by ``auto_footprint``).  Returns [N,3,res,res] (or [N,res,res,3]).
+
+    ``options``: a ``_lib.RenderOptions`` (accuracy / cost constants, default ``_lib.default_render_options()``).
+    ``flat=True`` evaluates the same sum pair by pair (``drm_render_refmaps_flat``, the validation path; any S in 1..16).
+    ``check_status=True`` synchronises and raises if a traversal list overflowed or an env_index was out of range."""
     if not (isinstance(envmaps, torch.Tensor) and envmaps.is_cuda):
         raise RuntimeError("envmaps must be a CUDA tensor: drmnet_b200 has no CPU path")
     if envmaps.dim() != 4 or envmaps.shape[-1] != 3:
@@ -121,16 +126,29 @@ def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor
         footprint_S, per_render = per_render[0], None
 
     def launch(S, zz, vv, ee, ff, oo):
+        import ctypes
         n = zz.shape[0]
         L = _lib.lib()
-        nbytes = L.drm_render_workspace_bytes(n, B, He, We, int(res), int(S))
+        nbytes = (L.drm_render_flat_workspace_bytes if flat else L.drm_render_workspace_bytes)(n, B, He, We, int(res), int(S))
         if nbytes == 0:
             raise ValueError(f"render_batch: unsupported sizes N={n} B={B} He={He} We={We} res={res} S={S}")
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _lib.check(L.drm_render_refmaps(envmaps.data_ptr(), B, He, We, ee.data_ptr(), zz.data_ptr(), vv.data_ptr(),
-                                        ff.data_ptr() if ff is not None else None, n, int(res), int(S),
-                                        float(alpha_min), int(channel_first), oo.data_ptr(), ws.data_ptr(),
-                                        ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+        stream = torch.cuda.current_stream(device).cuda_stream
+        args = (envmaps.data_ptr(), B, He, We, ee.data_ptr(), zz.data_ptr(), vv.data_ptr(),
+                ff.data_ptr() if ff is not None else None, n, int(res), int(S), float(alpha_min), int(channel_first),
+                oo.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        if flat:
+            _lib.check(L.drm_render_refmaps_flat(*args))
+            return
+        _lib.check(L.drm_render_refmaps_opts(*args, ctypes.byref(options) if options is not None else None))
+        if check_status:
+            st = (ctypes.c_int * 16)()
+            _lib.check(L.drm_render_status(ws.data_ptr(), st, stream))
+            torch.cuda.current_stream(device).synchronize()
+            render_batch.last_status = list(st)
+            if st[0]:
+                raise RuntimeError(f"render_batch: status {st[0]} (1: hand-over list overflow, 2: env_index out of range, "
+                                   f"4: traversal stack overflow); high-water marks {list(st)[1:]}")
 
     with torch.cuda.device(device):
         if per_render is None:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DRM_VERSION 100 /* major*10000 + minor*100 + patch */
+#define DRM_VERSION 200 /* major*10000 + minor*100 + patch */
 
 enum {
     DRM_OK = 0,
@@ -49,7 +49,7 @@ int64_t drm_launch_count(void);
  *              (utils/mitsuba3_utils.py:237-242); unnamed parameters carry the scene defaults 0,0,0,0,0,1 (:348-361)
  *   view3      [N, 3] fp32 camera position (any positive length; the sensor looks at the origin, up = +Y, :235-236)
  *   flip       [N] uint8 (may be NULL = no flip): mirrors the refmap columns (:38-40)
- *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117); 1..16
+ *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117); 1, 2, 4, 8 or 16
  *   alpha_min  lower clamp of the GGX alpha = roughness^2; <= 0 selects max(1e-3, 1.25*pi/He)
  *   channel_first  0: out [N, res, res, 3];  1: out [N, 3, res, res]   (:196-198)
  *   out        fp32 (device)
@@ -60,6 +60,52 @@ int drm_render_refmaps(const float* env, int B, int He, int We,
                        const int32_t* env_index, const float* z6, const float* view3, const uint8_t* flip,
                        int N, int res, int footprint_S, float alpha_min, int channel_first,
                        float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Accuracy / cost constants of the hierarchical evaluation.  The defaults hold the result within 1e-4
+ * (relative L2) of the full sum; they are arguments, not process environment: the library reads no environment variable. */
+typedef struct DrmRenderOptions {
+    float kappa;            /* a pyramid cell of half-vector radius r serves a block of normals at distance d when
+                               r <= kappa * sqrt(alpha^2 + d^2) ... */
+    float rcap;             /* ... and r <= rcap (radians) */
+    float horizon;          /* cells wider than this (radians) are refined where they straddle the horizon n.d = 0 */
+    float kappa_diffuse;    /* diffuse lobe: largest cell radius (radians) */
+    float horizon_diffuse;  /* diffuse lobe: the same horizon rule */
+    float level_scale;      /* scale of the distances beyond which a coarser footprint lattice is used (passes >= 1) */
+    float level_scale0;     /* the same for the 1x1 lattice when it carries the cell covariance */
+    int pixel_covariance;   /* pass 0 nodes carry the covariance of the refmap cell (fourth-order 1x1 lattice) */
+    int full_second_order;  /* second-order terms of G1(n.d) and the horizon clamp per cell (needed by rough lobes) ... */
+    float alpha_full2;      /* ... for renders with alpha >= this */
+    float hand_over;        /* a cell too near for a pass's lattice goes to the next pass once its radius is below
+                               hand_over * (that lattice's distance); larger cells are refined first */
+    float limb_nv;          /* blocks of normals with min n.v below max(limb_nv, limb_x * alpha) ... */
+    float limb_boost;       /* ... use lattice distances scaled by this (the cell average converges later at the limb) ... */
+    float limb_x;           /* ... and hand everything that comes near down to the render's own lattice */
+} DrmRenderOptions;
+
+void drm_render_default_options(DrmRenderOptions* opts);
+
+/* drm_render_refmaps with explicit options (opts == NULL: the defaults). */
+int drm_render_refmaps_opts(const float* env, int B, int He, int We,
+                            const int32_t* env_index, const float* z6, const float* view3, const uint8_t* flip,
+                            int N, int res, int footprint_S, float alpha_min, int channel_first,
+                            float* out, void* workspace, size_t workspace_bytes, void* cuda_stream,
+                            const DrmRenderOptions* opts);
+
+/* Copies the 16 status words of a finished (or enqueued: the copy is stream-ordered) render to status_host[16]:
+ * [0] flags, 0 = clean: bit 0 = the pool of hand-over lists ran out (result incomplete), bit 1 = an env_index was out of
+ * range, bit 2 = a traversal stack overflowed (result incomplete); [1] deepest traversal stack; [2..6] longest hand-over
+ * list written by passes 0..4; [8..11] chunks of 128 ints the passes 0..3 took from their pools. */
+int drm_render_status(const void* workspace, int* status_host, void* cuda_stream);
+
+/* Single-level evaluation of the same sum: every (sub-normal, texel) pair, S x S lattice, texels streamed by TMA
+ * (round-1 kernel).  ~1e4 times more work than drm_render_refmaps; the validation path for whole images at sizes the
+ * fp64 oracle cannot reach, footprint_S in 1..16 (any integer). */
+size_t drm_render_flat_workspace_bytes(int N, int B, int He, int We, int res, int footprint_S);
+
+int drm_render_refmaps_flat(const float* env, int B, int He, int We,
+                            const int32_t* env_index, const float* z6, const float* view3, const uint8_t* flip,
+                            int N, int res, int footprint_S, float alpha_min, int channel_first,
+                            float* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Image -> refmap scatter, batched over B images through `offsets`.

@@ -86,6 +86,79 @@ static void camera_frame(const double* view, double* vhat, double* left, double*
     upp[2] = fwd[0] * left[1] - fwd[1] * left[0];
 }
 
+/* pixel-independent terms of every record: 1/|v+d|, v.h, F_c(v.h) */
+static double* precompute_records(const double* rec_dir, long T, const double* vhat, double m, const double* base,
+                                  double eta) {
+    double* pre = (double*)malloc(sizeof(double) * (size_t)T * 6);
+    if (!pre) return NULL;
+    for (long t = 0; t < T; ++t) {
+        const double* d = rec_dir + 3 * t;
+        double vd = vhat[0] * d[0] + vhat[1] * d[1] + vhat[2] * d[2];
+        double len2 = 2.0 + 2.0 * vd; /* |v + d|^2 */
+        double inv_len = len2 > 1e-30 ? 1.0 / sqrt(len2) : 0.0;
+        double vh = (1.0 + vd) * inv_len; /* v.h = d.h */
+        double Fd = fresnel_dielectric(vh, eta);
+        double sw = schlick_weight(vh);
+        pre[6 * t + 0] = inv_len;
+        pre[6 * t + 1] = vh;
+        for (int c = 0; c < 3; ++c)
+            pre[6 * t + 2 + c] = (1.0 - m) * Fd + m * (base[c] + (1.0 - base[c]) * sw);
+        pre[6 * t + 5] = 0.0;
+    }
+    return pre;
+}
+
+/* one refmap cell (i, j): S x S Gauss-Legendre sub-normals x every record */
+static void render_cell(int i, int j, const double* rec_dir, const double* rec_E, const double* pre, long T,
+                        const double* vhat, const double* left, const double* upp, int flip, double cell, int S,
+                        const double* gl_x, const double* gl_w, double alpha, double m, double rough,
+                        const double* base, int terms, double* acc) {
+    acc[0] = acc[1] = acc[2] = 0.0;
+    for (int a = 0; a < S; ++a)
+        for (int b = 0; b < S; ++b) {
+            double th = (i + 0.5 + 0.5 * gl_x[a]) * cell;
+            double ph = (j + 0.5 + 0.5 * gl_x[b]) * cell;
+            double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
+            double lx = flip ? -st * cp : st * cp;
+            double n[3];
+            for (int k = 0; k < 3; ++k) n[k] = lx * left[k] + ct * upp[k] + st * sp * vhat[k];
+            double nv = n[0] * vhat[0] + n[1] * vhat[1] + n[2] * vhat[2];
+            if (nv <= 0.0) continue;
+            double g1v = smith_g1(nv, alpha);
+            double Fi = schlick_weight(nv);
+            double s_acc[3] = {0, 0, 0}, d_acc[3] = {0, 0, 0};
+            for (long t = 0; t < T; ++t) {
+                const double* d = rec_dir + 3 * t;
+                double nd = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+                if (nd <= 0.0) continue;
+                const double* p = pre + 6 * t;
+                const double* E = rec_E + 3 * t;
+                if (terms & 1) {
+                    double nh = (nv + nd) * p[0];
+                    double c2 = nh * nh;
+                    double q = c2 + (1.0 - c2) / (alpha * alpha);
+                    double D = 1.0 / (M_PI * alpha * alpha * q * q);
+                    if (D * nh <= 1e-20) D = 0.0;
+                    double w = D * g1v * smith_g1(nd, alpha) / (4.0 * nv);
+                    s_acc[0] += w * p[2] * E[0];
+                    s_acc[1] += w * p[3] * E[1];
+                    s_acc[2] += w * p[4] * E[2];
+                }
+                if (terms & 2) {
+                    double Fo = schlick_weight(nd);
+                    double Rr = 2.0 * rough * p[1] * p[1];
+                    double w = nd * ((1.0 - 0.5 * Fi) * (1.0 - 0.5 * Fo) + Rr * (Fo + Fi + Fo * Fi * (Rr - 1.0)));
+                    d_acc[0] += w * E[0];
+                    d_acc[1] += w * E[1];
+                    d_acc[2] += w * E[2];
+                }
+            }
+            double wq = gl_w[a] * gl_w[b];
+            for (int c = 0; c < 3; ++c)
+                acc[c] += wq * (s_acc[c] + (1.0 - m) * base[c] / M_PI * d_acc[c]);
+        }
+}
+
 /*
  * z6 = [metallic, base R, base G, base B, roughness, specular] (already clipped to [0,1]).
  * gl_x / gl_w: S Gauss-Legendre nodes on [-1,1] and weights normalised to sum 1.
@@ -104,81 +177,46 @@ int drm_oracle_render_records(const double* rec_dir, const double* rec_E, long T
     const double eta = 2.0 / (1.0 - sqrt(0.08 * specular)) - 1.0;
     double vhat[3], left[3], upp[3];
     camera_frame(view3, vhat, left, upp);
-
-    /* per-record, pixel-independent terms */
-    double* pre = (double*)malloc(sizeof(double) * (size_t)T * 6);
+    double* pre = precompute_records(rec_dir, T, vhat, m, base, eta);
     if (!pre) return -1;
-    for (long t = 0; t < T; ++t) {
-        const double* d = rec_dir + 3 * t;
-        double vd = vhat[0] * d[0] + vhat[1] * d[1] + vhat[2] * d[2];
-        double len2 = 2.0 + 2.0 * vd; /* |v + d|^2 */
-        double inv_len = len2 > 1e-30 ? 1.0 / sqrt(len2) : 0.0;
-        double vh = (1.0 + vd) * inv_len; /* v.h = d.h */
-        double Fd = fresnel_dielectric(vh, eta);
-        double sw = schlick_weight(vh);
-        pre[6 * t + 0] = inv_len;
-        pre[6 * t + 1] = vh;
-        for (int c = 0; c < 3; ++c)
-            pre[6 * t + 2 + c] = (1.0 - m) * Fd + m * (base[c] + (1.0 - base[c]) * sw);
-        pre[6 * t + 5] = 0.0;
-    }
-
     const double cell = M_PI / res;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int pix = 0; pix < res * res; ++pix) {
         int i = pix / res, j = pix % res;
-        double acc[3] = {0, 0, 0};
         if (window && (i < window[0] || i >= window[1] || j < window[2] || j >= window[3])) {
             out[3 * pix + 0] = out[3 * pix + 1] = out[3 * pix + 2] = 0.0;
             continue;
         }
-        for (int a = 0; a < S; ++a)
-            for (int b = 0; b < S; ++b) {
-                double th = (i + 0.5 + 0.5 * gl_x[a]) * cell;
-                double ph = (j + 0.5 + 0.5 * gl_x[b]) * cell;
-                double st = sin(th), ct = cos(th), sp = sin(ph), cp = cos(ph);
-                double lx = flip ? -st * cp : st * cp;
-                double n[3];
-                for (int k = 0; k < 3; ++k) n[k] = lx * left[k] + ct * upp[k] + st * sp * vhat[k];
-                double nv = n[0] * vhat[0] + n[1] * vhat[1] + n[2] * vhat[2];
-                if (nv <= 0.0) continue;
-                double g1v = smith_g1(nv, alpha);
-                double Fi = schlick_weight(nv);
-                double s_acc[3] = {0, 0, 0}, d_acc[3] = {0, 0, 0};
-                for (long t = 0; t < T; ++t) {
-                    const double* d = rec_dir + 3 * t;
-                    double nd = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
-                    if (nd <= 0.0) continue;
-                    const double* p = pre + 6 * t;
-                    const double* E = rec_E + 3 * t;
-                    if (terms & 1) {
-                        double nh = (nv + nd) * p[0];
-                        double c2 = nh * nh;
-                        double q = c2 + (1.0 - c2) / (alpha * alpha);
-                        double D = 1.0 / (M_PI * alpha * alpha * q * q);
-                        if (D * nh <= 1e-20) D = 0.0;
-                        double w = D * g1v * smith_g1(nd, alpha) / (4.0 * nv);
-                        s_acc[0] += w * p[2] * E[0];
-                        s_acc[1] += w * p[3] * E[1];
-                        s_acc[2] += w * p[4] * E[2];
-                    }
-                    if (terms & 2) {
-                        double Fo = schlick_weight(nd);
-                        double Rr = 2.0 * rough * p[1] * p[1];
-                        double w = nd * ((1.0 - 0.5 * Fi) * (1.0 - 0.5 * Fo) + Rr * (Fo + Fi + Fo * Fi * (Rr - 1.0)));
-                        d_acc[0] += w * E[0];
-                        d_acc[1] += w * E[1];
-                        d_acc[2] += w * E[2];
-                    }
-                }
-                double wq = gl_w[a] * gl_w[b];
-                for (int c = 0; c < 3; ++c)
-                    acc[c] += wq * (s_acc[c] + (1.0 - m) * base[c] / M_PI * d_acc[c]);
-            }
-        out[3 * pix + 0] = acc[0];
-        out[3 * pix + 1] = acc[1];
-        out[3 * pix + 2] = acc[2];
+        render_cell(i, j, rec_dir, rec_E, pre, T, vhat, left, upp, flip, cell, S, gl_x, gl_w, alpha, m, rough, base,
+                    terms, out + 3 * pix);
     }
+    free(pre);
+    return 0;
+}
+
+/*
+ * The same evaluation for a list of cells: cells = [ncells][2] (row i, column j), out = [ncells][3] doubles.
+ * Whole-image parity at the headline size is checked on a strided subset of the cells (every 8th row / column plus
+ * the last ones), which keeps the fp64 brute force to minutes per render.
+ */
+int drm_oracle_render_cells(const double* rec_dir, const double* rec_E, long T,
+                            const double* z6, const double* view3, int flip,
+                            int res, int S, const double* gl_x, const double* gl_w,
+                            double alpha_min, int terms, const int* cells, int ncells, double* out) {
+    const double m = z6[0], rough = z6[4], specular = z6[5];
+    const double base[3] = {z6[1], z6[2], z6[3]};
+    double alpha = rough * rough;
+    if (alpha < alpha_min) alpha = alpha_min;
+    const double eta = 2.0 / (1.0 - sqrt(0.08 * specular)) - 1.0;
+    double vhat[3], left[3], upp[3];
+    camera_frame(view3, vhat, left, upp);
+    double* pre = precompute_records(rec_dir, T, vhat, m, base, eta);
+    if (!pre) return -1;
+    const double cell = M_PI / res;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int e = 0; e < ncells; ++e)
+        render_cell(cells[2 * e], cells[2 * e + 1], rec_dir, rec_E, pre, T, vhat, left, upp, flip, cell, S, gl_x, gl_w,
+                    alpha, m, rough, base, terms, out + 3 * e);
     free(pre);
     return 0;
 }

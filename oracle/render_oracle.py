@@ -43,6 +43,10 @@ def _load():
                                                    ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
                                                    ctypes.POINTER(ctypes.c_int), dp]
         _lib.drm_oracle_render_records.restype = ctypes.c_int
+        _lib.drm_oracle_render_cells.argtypes = [dp, dp, ctypes.c_long, dp, dp, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_int), ctypes.c_int, dp]
+        _lib.drm_oracle_render_cells.restype = ctypes.c_int
         _lib.drm_oracle_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -124,6 +128,38 @@ def render_oracle(env, z, view, res, *, names=None, S=1, flip=False, alpha_min=N
         alpha_min = default_alpha_min(env.shape[0])
     dirs, E = env_records(env)
     return render_records(dirs, E, z6, view, res, S=S, flip=flip, alpha_min=alpha_min, terms=terms, window=window)
+
+
+def strided_cells(res: int, stride: int = 8) -> np.ndarray:
+    """Every ``stride``-th row / column of the refmap plus the last one ([ncells,2] int32, row-major): the subset on
+    which whole-image parity at the headline size is checked; it contains rows / columns 0 and res-1 (the limb)."""
+    idx = sorted(set(range(0, res, stride)) | {res - 1})
+    return np.array([(i, j) for i in idx for j in idx], dtype=np.int32)
+
+
+def render_oracle_cells(env, z, view, res, cells, *, names=None, S=1, flip=False, alpha_min=None, terms=3) -> np.ndarray:
+    """Canonical render of the listed cells only: [ncells,3] fp64 (cells = [ncells,2] rows / columns)."""
+    lib = _load()
+    env = np.asarray(env)
+    if names is None:
+        names = list(_NAME_TO_SLOT)
+    z6 = np.ascontiguousarray(z_from_named(z, names))
+    if alpha_min is None:
+        alpha_min = default_alpha_min(env.shape[0])
+    dirs, E = env_records(env)
+    view = np.ascontiguousarray(view, dtype=np.float64)
+    cells = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
+    gx, gw = gauss_legendre(S)
+    out = np.zeros((cells.shape[0], 3), np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = lib.drm_oracle_render_cells(dirs.ctypes.data_as(dp), E.ctypes.data_as(dp), dirs.shape[0],
+                                     z6.ctypes.data_as(dp), view.ctypes.data_as(dp), int(bool(flip)), int(res), int(S),
+                                     gx.ctypes.data_as(dp), gw.ctypes.data_as(dp), float(alpha_min), int(terms),
+                                     cells.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(cells.shape[0]),
+                                     out.ctypes.data_as(dp))
+    if rc != 0:
+        raise MemoryError("render oracle allocation failed")
+    return out
 
 
 def rel_l2(a, b) -> float:

@@ -1,0 +1,33 @@
+"""One golden case under several option sets (development tool): tree_case.py <npz> <case index>"""
+import sys
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from drmnet_b200 import _lib
+from drmnet_b200.renderer import render_batch
+from drmnet_b200.synth import synthetic_envmap
+g = np.load(sys.argv[1]); 
+for i in [int(x) for x in sys.argv[2:]]:
+    He, We, res = int(g["He"]), int(g["We"]), int(g["res"])
+    seed, zi, vi, S, nc = [int(x) for x in g["meta"][i]]
+    env = torch.from_numpy(synthetic_envmap(He, We, seed=seed)).cuda()[None]
+    z = torch.tensor(g["z"][i], dtype=torch.float32)[None]; v = torch.tensor(g["view"][i], dtype=torch.float32)[None]
+    cl = g["cells"][i][:nc]; ref = g["values"][i][:nc]
+    print(f"case {i}: seed {seed} z{zi} v{vi} S={S} rough {float(z[0,4]):.3f}")
+    def run(name, flat=False, **kw):
+        o = _lib.default_render_options()
+        for k, val in kw.items(): setattr(o, k, val)
+        out = render_batch(env, z, v, res=res, footprint_S=S, alpha_min=float(g["alpha_min"]), channel_first=False,
+                           options=o, flat=flat, check_status=not flat)[0].double().cpu().numpy()
+        got = out[cl[:, 0], cl[:, 1]]
+        e = np.abs(got - ref).max(1); k = int(e.argmax())
+        print(f"  {name:28s} rel-L2 {np.linalg.norm(got-ref)/np.linalg.norm(ref):.2e} max/peak {e.max()/np.abs(ref).max():.2e} at cell {cl[k]} marks {getattr(render_batch,'last_status',None)}")
+    run("flat", flat=True)
+    run("default")
+    run("level_scale x2", level_scale=0.6, level_scale0=0.3)
+    run("level_scale x3", level_scale=0.9, level_scale0=0.45)
+    run("ls x2, no limb", level_scale=0.6, level_scale0=0.3, limb_boost=1.0)
+    run("hand 1e6", hand_over=1e6)
+    run("kappa 0.05", kappa=0.05)
+    run("no pixcov", pixel_covariance=0)

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.drm_version() == 100
+    assert lib.drm_version() == 200
     assert isinstance(lib.drm_last_error(), bytes)
 
 
@@ -36,6 +36,8 @@ def test_workspace_queries(lib):
     assert lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1) > 0
     assert lib.drm_render_workspace_bytes(64, 64, 1000, 2000, 128, 1) > lib.drm_render_workspace_bytes(64, 1, 1000, 2000, 128, 1)
     assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 17) == 0
+    assert lib.drm_render_workspace_bytes(1, 1, 1000, 2000, 128, 3) == 0  # the lattices are 1, 2, 4, 8, 16
+    assert lib.drm_render_flat_workspace_bytes(1, 1, 1000, 2000, 128, 3) > 0  # the validation path takes any S <= 16
     assert lib.drm_render_workspace_bytes(0, 1, 1000, 2000, 128, 1) == 0
     a = lib.drm_img2refmap_workspace_bytes(27774, 1, 128, 3.14159 / 256)
     b = lib.drm_img2refmap_workspace_bytes(27774, 1, 128, 3.14159 / 64)
@@ -52,6 +54,12 @@ def test_argument_validation_without_a_device(lib):
     assert rc == _lib.DRM_EINVAL and b"C=7" in lib.drm_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)
+
+
+def test_render_options_defaults(lib):
+    o = _lib.default_render_options()
+    assert 0.05 <= o.kappa <= 0.2 and o.rcap > 0 and o.pixel_covariance == 1 and o.full_second_order == 1
+    assert o.level_scale > 0 and o.hand_over > 0 and o.limb_boost >= 1
 
 
 def test_python_wrappers_refuse_cpu_tensors():
