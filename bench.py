@@ -1,25 +1,35 @@
 #!/usr/bin/env python
-"""Headline benchmark: refmaps rendered / s (128x128 refmaps, 2000x1000 envmaps) -- BASELINE.json metric.
+"""Benchmarks of the DRMNet rendering hot path on B200 -- BASELINE.json metric and configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 64] [--footprint auto|S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload render|img2refmap|synth|sampling] [--batch B] [--footprint auto|S]
 
-A step is one pass of the hot path over one batch: BASELINE config[1], 64 synthetic 2000x1000 envmaps x random BRDF
-parameters (z ~ U[0,1]^6, dataset/parametricrefmap.py:105; 64 equatorial views, :114-116) -> 64 refmaps of 128x128, per
-GPU (weak scaling: every rank owns its own 64 envmaps; the rendered refmaps are all-gathered over NCCL).
+workload  (a step is one pass of the hot path over one batch of synthetic input, per GPU; weak scaling over ranks)
+  render      BASELINE config[1] -- THE HEADLINE: 64 synthetic 2000x1000 envmaps x random BRDF parameters
+              (z ~ U[0,1]^6, dataset/parametricrefmap.py:105; 64 equatorial views, :114-116) -> 64 refmaps of 128x128
+  img2refmap  secondary metric: 64 sphere images of 512x512 (~206k masked px each) -> 64 refmaps, res 128
+  synth       BASELINE config[2]: training-data synthesis, batch 20 x {LrK, Lrk, Lrkm1} (models/drmnet.py:523-569)
+              through callers.synthesize_refmaps (render + luminance normalisation + log transform)
+  sampling    BASELINE config[3]: per-step re-render of a sampling batch of 32: r0 -> 128x256 envmap (r0toenvmap,
+              models/drmnet.py:931-941) -> render at the current z (DRMNet.reconstruct, :943-952)
 
-value     device-timed whole-job throughput, inputs resident in HBM (1.5 GB of envmaps per GPU: larger than L2)
-e2e       same metric through the public API (drmnet_b200.renderer.render_batch) with HOST buffers: pinned envmaps
-          copied host->device and the refmaps copied back inside the timed region
-roofline  algorithmic bytes (24 196 648 B per refmap) / CUDA-event time of the gather launches, against the
-          measured HBM copy peak; the kernel is FP32/MUFU-pipe bound, so `fp32_pipe` carries the instruction-rate view
-cpu_baseline  the fp64 oracle port on the host cores on a bounded sample of the same workload (rank 0 only)
+value     device-timed whole-job throughput, inputs resident in HBM (larger than L2 for render / img2refmap / synth)
+e2e       the same metric through the public API with HOST buffers: pinned inputs copied host->device and the results
+          copied back inside the timed region; median of >= 5 steps
+roofline  algorithmic bytes of the step / CUDA-event time of the step on the launching stream, against the measured HBM
+          copy peak (MEASURED_PEAKS.json).  The render is bound by the FP32 issue rate, not by HBM: `issue`
+          carries the instruction-rate view from the committed ncu captures
+cpu_baseline  render: the fp64 oracle port (C + OpenMP, all host cores) on a bounded sample of the same workload;
+              img2refmap: the numpy oracle port on one image of the batch (rank 0 only)
+Multi-GPU: every rank owns its own envmaps; the rendered refmaps are gathered by ONE equal-count all_gather on a side
+stream (drmnet_b200.dist.RefmapGather); `rank_ms` lists every rank's own step time.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -31,20 +41,12 @@ sys.path.insert(0, str(ROOT))
 
 HE, WE, RES = 1000, 2000, 128
 ALG_BYTES_PER_REFMAP = HE * WE * 3 * 4 + RES * RES * 3 * 4 + 40  # 24 196 648
-METRIC = "refmaps rendered/sec (128^2, 2000x1000 envmap)"
-
-
-def measured_traffic(batch, footprint):
-    """(DRAM bytes of one step, pipe utilisation of the gather kernel) from the committed ncu captures
-    (profiles/r1_traffic.json), for the workload they were taken on."""
-    p = ROOT / "profiles" / "r1_traffic.json"
-    try:
-        d = json.loads(p.read_text())
-        if d["workload"] == {"batch_per_gpu": batch, "footprint": footprint}:
-            return d["dram_bytes_per_step"], d.get("ncu_gather_pipes")
-    except Exception:
-        pass
-    return None, None
+METRICS = {
+    "render": ("refmaps rendered/sec (128^2, 2000x1000 envmap)", "refmaps/s"),
+    "img2refmap": ("img2refmaps/sec (res 128, ~206k px per image)", "img2refmaps/s"),
+    "synth": ("refmaps synthesised/sec (training batch 20 x 3, 2000x1000 envmap, normalised + log)", "refmaps/s"),
+    "sampling": ("refmaps re-rendered/sec (sampling batch 32, 128x256 envmap from r0toenvmap)", "refmaps/s"),
+}
 
 
 def hbm_peak():
@@ -55,6 +57,15 @@ def hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_summary(workload):
+    """Instruction-rate view of the dominant kernel from the committed ncu capture of this workload (profiles/)."""
+    p = ROOT / "profiles" / "r2_issue.json"
+    try:
+        return json.loads(p.read_text()).get(workload)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -105,18 +116,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(batch: int, rank: int, device):
-    import torch
-    from drmnet_b200.synth import sample_brdf, sample_view, synthetic_envmap
-    base = 1000 + rank * batch
-    envs = torch.empty((batch, HE, WE, 3), dtype=torch.float32, device=device)
-    for b in range(batch):
-        envs[b] = synthetic_envmap(HE, WE, seed=base + b, device=device, as_numpy=False)
-    z = torch.stack([sample_brdf(base + b) for b in range(batch)])
-    view = torch.stack([sample_view(base + b) for b in range(batch)])
-    return envs, z, view
-
-
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads: each returns dict(step=callable -> local result tensor, e2e_step=callable, units=per-rank units per step,
+#                              alg_bytes=per-rank algorithmic bytes per step, h2d=, d2h=, config=, dtype=, gather=bool)
+# ---------------------------------------------------------------------------------------------------------------------
 def footprints(z, mode):
     from drmnet_b200.renderer import auto_footprint, default_alpha_min
     if mode == "auto":
@@ -124,13 +127,169 @@ def footprints(z, mode):
     return [int(mode)] * z.shape[0]
 
 
+def wl_render(args, rank, dev):
+    import torch
+    from drmnet_b200.renderer import render_batch
+    from drmnet_b200.synth import sample_brdf, sample_view, synthetic_envmap
+    batch = args.batch or 64
+    base = 1000 + rank * batch
+    envs = torch.empty((batch, HE, WE, 3), dtype=torch.float32, device=dev)
+    for b in range(batch):
+        envs[b] = synthetic_envmap(HE, WE, seed=base + b, device=dev, as_numpy=False)
+    z = torch.stack([sample_brdf(base + b) for b in range(batch)])
+    view = torch.stack([sample_view(base + b) for b in range(batch)])
+    S_list = footprints(z, args.footprint)
+    z_d, view_d = z.to(dev), view.to(dev)
+    out = torch.empty((batch, 3, RES, RES), dtype=torch.float32, device=dev)
+
+    def step():
+        return render_batch(envs, z_d, view_d, res=RES, footprint_S=S_list, out=out)
+
+    host_envs = envs.cpu().pin_memory()
+    host_out = torch.empty((batch, 3, RES, RES), dtype=torch.float32).pin_memory()
+    host_z, host_view = z.pin_memory(), view.pin_memory()
+
+    def e2e_step():
+        d_env = host_envs.to(dev, non_blocking=True)
+        r = render_batch(d_env, host_z.to(dev, non_blocking=True), host_view.to(dev, non_blocking=True), res=RES,
+                         footprint_S=S_list)
+        host_out.copy_(r, non_blocking=True)
+        torch.cuda.synchronize()
+
+    return dict(step=step, e2e_step=e2e_step, units=batch, alg_bytes=batch * ALG_BYTES_PER_REFMAP, gather=True,
+                h2d=host_envs.numel() * 4 + host_z.numel() * 4 + host_view.numel() * 4, d2h=host_out.numel() * 4,
+                dtype="f32",
+                config={"workload": "config[1]: batched parametric refmap render, 64 synthetic 2000x1000 envmaps x random "
+                                    "BRDF params -> 128x128 refmaps per GPU", "batch_per_gpu": batch,
+                        "footprint": args.footprint,
+                        "footprint_S_histogram": {str(s): S_list.count(s) for s in sorted(set(S_list))},
+                        "l2": "inputs larger than L2 (1.5 GB of envmaps per GPU)"},
+                cpu=lambda: cpu_port_sample(batch, 8, args.footprint))
+
+
+def wl_img2refmap(args, rank, dev):
+    import numpy as np
+    import torch
+    from drmnet_b200.img2refmap import img2refmap_batch
+    from drmnet_b200.synth import sphere_image_inputs
+    batch = args.batch or 64
+    res, thr = 128, float(np.pi / 128 / 2)
+    cols, nrms, offs = [], [], [0]
+    for b in range(batch):
+        c, n = sphere_image_inputs(256, seed=100 + (rank * batch + b) % 8)
+        cols.append(c); nrms.append(n); offs.append(offs[-1] + len(c))
+    h_col = torch.from_numpy(np.concatenate(cols)).pin_memory()
+    h_nrm = torch.from_numpy(np.concatenate(nrms)).pin_memory()
+    colors, normals = h_col.to(dev), h_nrm.to(dev)
+    offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+    total_n = colors.shape[0]
+    h_map = torch.empty((batch, res, res, 3), dtype=torch.float32).pin_memory()
+    h_mask = torch.empty((batch, res, res), dtype=torch.bool).pin_memory()
+
+    def step():
+        return img2refmap_batch(colors, normals, offsets, res, thr)[0]
+
+    def e2e_step():
+        o = img2refmap_batch(h_col.to(dev, non_blocking=True), h_nrm.to(dev, non_blocking=True), offsets, res, thr)
+        h_map.copy_(o[0], non_blocking=True)
+        h_mask.copy_(o[1], non_blocking=True)
+        torch.cuda.synchronize()
+
+    def cpu():
+        from oracle.img2refmap_oracle import img2refmap_oracle
+        t0 = time.perf_counter()
+        img2refmap_oracle(cols[0], nrms[0], res, thr)
+        dt = time.perf_counter() - t0
+        return 1.0 / dt, dt, 1, (f"numpy port of utils/img2refmap.py:6-37 (oracle/img2refmap_oracle.py), one image of the "
+                                 f"batch ({len(cols[0])} px) in {dt:.2f} s; the reference's own O(res^2 n) torch code took "
+                                 "3.6 s on 8 cores for a 27 774-px image (BASELINE.md)")
+
+    return dict(step=step, e2e_step=e2e_step, units=batch, alg_bytes=24 * total_n + batch * res * res * (13 + 8),
+                gather=False, h2d=(h_col.numel() + h_nrm.numel()) * 4, d2h=h_map.numel() * 4 + h_mask.numel(),
+                dtype="f32 compare / u32 keys",
+                config={"workload": "img2refmap: 64 sphere images of 512x512 (SURVEY 8d inputs (b),(c)) -> 64 refmaps, "
+                                    "res 128, thr pi/256", "batch_per_gpu": batch, "pixels_per_image": total_n // batch,
+                        "l2": "inputs larger than L2 (317 MB of pixels per GPU)"},
+                cpu=cpu)
+
+
+def wl_synth(args, rank, dev):
+    import torch
+    from drmnet_b200.callers import synthesize_refmaps
+    from drmnet_b200.renderer import B200RefMapRenderer
+    from drmnet_b200.synth import BRDF_PARAM_NAMES, sample_brdf, sample_view, schedule_point, synthetic_envmap
+    B = args.batch or 20
+    base = 2000 + rank * B
+    envs = torch.stack([synthetic_envmap(HE, WE, base + b, device=dev, as_numpy=False) for b in range(B)])
+    zK = torch.stack([sample_brdf(base + b) for b in range(B)])
+    sched = [schedule_point(zK[b], float(torch.rand((), generator=torch.Generator().manual_seed(base + b)))) for b in range(B)]
+    stacked_z = torch.stack([zK, torch.stack([s[2] for s in sched]).float(), torch.stack([s[3] for s in sched]).float()])
+    views = torch.stack([sample_view(base + b) for b in range(B)])
+    r = B200RefMapRenderer(refmap_res=RES, spp=256, denoise="simple", brdf_param_names=BRDF_PARAM_NAMES)
+    h_env = envs.cpu().pin_memory()
+    h_out = torch.empty((3, B, 3, RES, RES), dtype=torch.float32).pin_memory()
+
+    def step():
+        return torch.stack(synthesize_refmaps(r, stacked_z, envs, views)[0])
+
+    def e2e_step():
+        o = synthesize_refmaps(r, stacked_z, h_env.to(dev, non_blocking=True), views)[0]
+        h_out.copy_(torch.stack(o), non_blocking=True)
+        torch.cuda.synchronize()
+
+    return dict(step=step, e2e_step=e2e_step, units=3 * B, alg_bytes=B * HE * WE * 12 + 3 * B * (RES * RES * 12 + 40),
+                gather=False, h2d=h_env.numel() * 4, d2h=h_out.numel() * 4, dtype="f32",
+                config={"workload": "config[2]: training-data synthesis, batch 20 x {LrK, Lrk, Lrkm1} sharing envmap and "
+                                    "view, render + luminance normalisation + log transform", "batch_per_gpu": B,
+                        "renders_per_step_per_gpu": 3 * B, "l2": "inputs larger than L2 (480 MB of envmaps per GPU)"},
+                cpu=None)
+
+
+def wl_sampling(args, rank, dev):
+    import torch
+    from drmnet_b200.callers import r0toenvmap
+    from drmnet_b200.renderer import render_batch
+    from drmnet_b200.synth import Z0, sample_brdf, synthetic_envmap
+    B = args.batch or 32
+    one = torch.tensor([[0.0, 0.0, 1.1]])
+    basis = render_batch(torch.ones(1, 128, 256, 3, device=dev), torch.tensor([list(Z0)]), one, res=RES, footprint_S=2)[0]
+    env0 = synthetic_envmap(HE, WE, 3000 + rank, device=dev, as_numpy=False)[None]
+    r0 = render_batch(env0, torch.tensor([list(Z0)]), one, res=RES, footprint_S=4).expand(B, 3, RES, RES).contiguous()
+    z = torch.stack([sample_brdf(3000 + rank * B + b) for b in range(B)]).to(dev)
+    view = one.expand(B, 3).contiguous().to(dev)
+    rough = z[:, 4].clip(0, 1).tolist()
+    from drmnet_b200.renderer import auto_footprint, default_alpha_min
+    S_list = [auto_footprint(r, RES, default_alpha_min(128)) for r in rough]
+    h_r0 = r0.cpu().pin_memory()
+    h_out = torch.empty((B, 3, RES, RES), dtype=torch.float32).pin_memory()
+
+    def step():
+        env = r0toenvmap(r0, basis.clamp_min(1e-3), (128, 256)).contiguous()
+        return render_batch(env, z, view, res=RES, footprint_S=S_list)
+
+    def e2e_step():
+        env = r0toenvmap(h_r0.to(dev, non_blocking=True), basis.clamp_min(1e-3), (128, 256)).contiguous()
+        h_out.copy_(render_batch(env, z, view, res=RES, footprint_S=S_list), non_blocking=True)
+        torch.cuda.synchronize()
+
+    return dict(step=step, e2e_step=e2e_step, units=B, alg_bytes=B * (RES * RES * 12 * 2 + 128 * 256 * 12 * 2), gather=True,
+                h2d=h_r0.numel() * 4, d2h=h_out.numel() * 4, dtype="f32",
+                config={"workload": "config[3]: per-step re-render of a sampling batch of 32 (r0toenvmap -> 128x256 envmap -> "
+                                    "render at the current z); the U-Nets are stock PyTorch and not part of the step",
+                        "batch_per_gpu": B, "l2": "flushed between steps (a 256 MB buffer is written)"},
+                cpu=None, flush_l2=True)
+
+
+WORKLOADS = {"render": wl_render, "img2refmap": wl_img2refmap, "synth": wl_synth, "sampling": wl_sampling}
+
 _CPU_ENV = None
 
 
 def cpu_port_sample(batch, n_renders, footprint):
-    """The fp64 oracle port (C + OpenMP, all host cores) on a bounded sample of the workload: the first `n_renders`
-    renders of rank 0's batch, each with its own footprint S, each on a k x k block of cells of the 128x128 refmap sized
-    so one render costs about a second (cost ~ cells x S^2 x texels).  refmaps/s = sum(cell fractions) / sum(times)."""
+    """The fp64 oracle port (C + OpenMP, all host cores) on a bounded sample of the render workload: the first
+    `n_renders` renders of rank 0's batch, each with its own footprint S, each on a k x k block of cells of the 128x128
+    refmap sized so one render costs about a second (cost ~ cells x S^2 x texels).  refmaps/s = sum(cell fractions) /
+    sum(times)."""
     from drmnet_b200.renderer import auto_footprint, default_alpha_min
     from drmnet_b200.synth import sample_brdf, sample_view, synthetic_envmap
     from oracle import render_oracle as ro
@@ -158,36 +317,48 @@ def cpu_port_sample(batch, n_renders, footprint):
 
 def run_reference(args):
     """--impl reference: the reference has no CPU renderer (Mitsuba cuda_ad_rgb is hard-coded, main.py:26) and Mitsuba
-    is unavailable; the timed arm is the oracle port on all host threads, each step a bounded sample of the workload."""
+    is unavailable; the timed arm is the oracle port on all host threads, each step a bounded sample of the workload.
+    For img2refmap the port is the numpy restatement of utils/img2refmap.py."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 4
+    metric, unit = METRICS[args.workload]
     vals, ms, cores, sample = [], [], 1, ""
     for it in range(args.warmup + args.steps):
-        v, t, cores, sample = cpu_port_sample(args.batch, per_step, args.footprint)
+        if args.workload == "img2refmap":
+            import numpy as np
+            from drmnet_b200.synth import sphere_image_inputs
+            from oracle.img2refmap_oracle import img2refmap_oracle
+            c, n = sphere_image_inputs(256, seed=100)
+            t0 = time.perf_counter()
+            img2refmap_oracle(c, n, 128, float(np.pi / 256))
+            t = time.perf_counter() - t0
+            v, cores, sample = 1.0 / t, 1, f"numpy port of utils/img2refmap.py, one image of {len(c)} px per step"
+        else:
+            v, t, cores, sample = cpu_port_sample(args.batch or 64, 4, args.footprint)
         if it >= args.warmup:
             vals.append(v); ms.append(t * 1e3)
     value = sum(vals) / len(vals)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "refmaps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config[1]: batched parametric refmap render, 2000x1000 envmaps -> 128x128 refmaps "
-                               "(bounded sample per step)", "batch_per_gpu": args.batch, "footprint": args.footprint},
-        "cpu_baseline": {"value": value, "unit": "refmaps/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "refmaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{args.workload} (bounded sample per step on the host cores)", "footprint": args.footprint},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="envmaps (= renders) per GPU per step")
-    ap.add_argument("--footprint", default="auto", help="'auto' (per render, from its roughness) or an int S")
+    ap.add_argument("--workload", default="render", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (0: the workload's own: 64 / 64 / 20 / 32)")
+    ap.add_argument("--footprint", default="auto", help="'auto' (per render, from its roughness) or 1, 2, 4, 8, 16")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -196,8 +367,7 @@ def main():
     import torch
     import torch.distributed as dist
     from drmnet_b200 import _lib
-    from drmnet_b200.dist import all_gather_refmaps
-    from drmnet_b200.renderer import render_batch
+    from drmnet_b200.dist import RefmapGather
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,109 +378,99 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-
-    batch = args.batch
-    envs, z, view = make_workload(batch, rank, dev)
-    S_list = footprints(z, args.footprint)
-    z_d, view_d = z.to(dev), view.to(dev)
-    out = torch.empty((batch, 3, RES, RES), dtype=torch.float32, device=dev)
-    ids = torch.arange(batch, device=dev) + rank * batch
+    W = WORKLOADS[args.workload](args, rank, dev)
+    units = W["units"]
+    gather = None
+    if world > 1 and W["gather"]:
+        ids = [torch.arange(units) + r * units for r in range(world)]  # a pure function of the rank: no count exchange
+        gather = RefmapGather(ids, units * world, dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if W.get("flush_l2") else None
 
     def step():
-        render_batch(envs, z_d, view_d, res=RES, footprint_S=S_list, out=out)
-        if world > 1:
-            return all_gather_refmaps(out, ids, batch * world)
-        return out
+        if flush is not None:
+            flush.zero_()
+        r = W["step"]()
+        if gather is not None:
+            gather.launch(r)  # side stream: the next step's kernels start while the blocks travel
+        return r
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step()
+    if gather is not None:
+        gather.result()
     barrier()
     launches0 = L.drm_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
         barrier()
-        torch.cuda.nvtx.range_push("drm_timed")
-        ev0.record()
-        for _ in range(args.steps):
+        ev[0].record()
+        for i in range(args.steps):
             step()
-        ev1.record()
+            ev[i + 1].record()
+        if gather is not None:
+            gather.result()
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+        else:
+            end = ev[-1]
         barrier()
-        torch.cuda.nvtx.range_pop()
-    ms = ev0.elapsed_time(ev1)
-    launches = (L.drm_launch_count() - launches0)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms_own = ev[0].elapsed_time(end)
+    launches = L.drm_launch_count() - launches0
+    t = torch.tensor([ms_own], dtype=torch.float64, device=dev)
+    all_ms = [t.clone() for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        dist.all_gather(all_ms, t)
+    rank_ms = [float(x.item()) / args.steps for x in all_ms]
+    ms = max(float(x.item()) for x in all_ms)
     ms_per_step = ms / args.steps
-    value = batch * world * args.steps / (ms / 1e3)
+    value = units * world * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timed region -------
-    # one pinned staging buffer of `chunk` envmaps is cycled so the pinned footprint stays bounded
-    host_envs = envs.cpu().pin_memory()
-    host_out = torch.empty((batch, 3, RES, RES), dtype=torch.float32).pin_memory()
-    host_z, host_view = z.pin_memory(), view.pin_memory()
-
-    def e2e_step():
-        d_env = host_envs.to(dev, non_blocking=True)
-        d_z = host_z.to(dev, non_blocking=True)
-        d_v = host_view.to(dev, non_blocking=True)
-        r = render_batch(d_env, d_z, d_v, res=RES, footprint_S=S_list)
-        host_out.copy_(r, non_blocking=True)
-        torch.cuda.synchronize()
-
-    e2e_steps = 1
-    e2e_step()
+    # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timed region -------------
+    W["e2e_step"]()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_times = []
+    for _ in range(max(5, args.e2e_steps)):
+        barrier()
+        t0 = time.perf_counter()
+        W["e2e_step"]()
+        barrier()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = torch.tensor([statistics.median(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = batch * world * e2e_steps / float(e2e_s.item())
-    h2d = host_envs.numel() * 4 + host_z.numel() * 4 + host_view.numel() * 4
-    d2h = host_out.numel() * 4
-    del host_envs
+    e2e_value = units * world / float(e2e_s.item())
 
     if rank == 0:
+        metric, unit = METRICS[args.workload]
         peak, peak_src = hbm_peak()
-        traffic, pipes = measured_traffic(batch, args.footprint)
-        # dominant kernel = render_gather_kernel: > 99 % of the step (see profiles/); achieved = algorithmic bytes of
-        # the renders of this rank / event time of the step on the launching stream
-        achieved = batch * ALG_BYTES_PER_REFMAP / (ms_per_step / 1e3) / 1e9
-        pairs = sum(s * s for s in S_list) * RES * RES * HE * WE  # (sub-normal, texel) pairs of the canonical sum
+        achieved = W["alg_bytes"] / (rank_ms[0] / 1e3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "refmaps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config[1]: batched parametric refmap render, 64 synthetic 2000x1000 envmaps x random "
-                                   "BRDF params -> 128x128 refmaps per GPU", "batch_per_gpu": batch,
-                       "footprint": args.footprint, "footprint_S_histogram": {str(s): S_list.count(s) for s in sorted(set(S_list))},
-                       "l2": "inputs larger than L2 (1.5 GB of envmaps per GPU)", "parallelism": f"dp{world}",
-                       "collective": "all_gather of rendered refmaps" if world > 1 else "none"},
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
+            "config": dict(W["config"], parallelism=f"dp{world}",
+                           collective="one equal-count all_gather of the results on a side stream" if gather else "none"),
+            "rank_ms": {"per_rank": rank_ms, "min": min(rank_ms), "max": max(rank_ms)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_step": batch * ALG_BYTES_PER_REFMAP,
-                         "peak_source": peak_src,
-                         "note": "kernel is FP32/MUFU-pipe bound (FMA pipe 60-71% busy, MUFU 48-56%, DRAM < 0.2%: profiles/r1_render_ncu_full_S*.csv), not HBM bound; "
-                                 "see DESIGN.md 5"},
-            "canonical_sum": {"pairs_per_step": pairs, "pairs_per_s_equivalent": pairs / (ms_per_step / 1e3),
-                              "note": "(sub-normal, texel) terms of the defining sum; footprint levels and the coarse "
-                                      "map evaluate far fewer"},
-            "ncu_gather_pipes": pipes,
-            "e2e": {"value": e2e_value, "unit": "refmaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                         "traffic": (ncu_summary(args.workload) or {}).get("dram_bytes_per_step"),
+                         "algorithmic_bytes_per_step": W["alg_bytes"], "peak_source": peak_src,
+                         "note": "whole step (every launch) on the launching stream; the render is bound by the FP32 issue rate, "
+                                 "not by HBM (DESIGN.md 5)" if args.workload != "img2refmap" else
+                                 "whole step (every launch) on the launching stream"},
+            "issue": ncu_summary(args.workload),
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": W["h2d"], "d2h_bytes_per_step": W["d2h"],
+                    "steps": len(e2e_times), "statistic": "median"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
-        if not args.no_cpu_baseline:
-            v, _, cores, sample = cpu_port_sample(batch, 8, args.footprint)
-            line["cpu_baseline"] = {"value": v, "unit": "refmaps/s", "cores": cores, "kind": "port", "sample": sample}
+        if not args.no_cpu_baseline and W.get("cpu"):
+            v, _, cores, sample = W["cpu"]()
+            line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -15,11 +15,13 @@ DRM_OK, DRM_EINVAL, DRM_EWORKSPACE, DRM_ECUDA, DRM_EUNSUPPORTED = 0, -1, -2, -3,
 
 class RenderOptions(ctypes.Structure):
     """DrmRenderOptions of include/drmrender.h: accuracy / cost constants of the hierarchical render."""
-    _fields_ = [("kappa", ctypes.c_float), ("rcap", ctypes.c_float), ("horizon", ctypes.c_float),
+    _fields_ = [("kappa", ctypes.c_float), ("rcap", ctypes.c_float), ("rcap_simple", ctypes.c_float),
+                ("horizon", ctypes.c_float),
                 ("kappa_diffuse", ctypes.c_float), ("horizon_diffuse", ctypes.c_float),
                 ("level_scale", ctypes.c_float), ("level_scale0", ctypes.c_float),
                 ("pixel_covariance", ctypes.c_int), ("full_second_order", ctypes.c_int), ("alpha_full2", ctypes.c_float), ("hand_over", ctypes.c_float), ("limb_nv", ctypes.c_float),
-                ("limb_boost", ctypes.c_float), ("limb_x", ctypes.c_float)]
+                ("limb_boost", ctypes.c_float), ("limb_x", ctypes.c_float), ("limb_hand", ctypes.c_float),
+                ("limb_ramp", ctypes.c_float), ("flat_scale", ctypes.c_float)]
 
 
 def default_render_options() -> "RenderOptions":

@@ -68,6 +68,7 @@ struct TreeArgs {
     const float4* pyr_d;   // [B][geom_d.cells][REC4]
     float* out;
     int* status;           // [0]: list / stack overflow flag
+    const int* env_used;   // [B] envmaps whose diffuse pyramid this call reads
     // hand-over lists: chains of CHUNK-int chunks ([0] next chunk or -1, [1] entries, [2..] entries) in a pool per pass
     const int* pool_in;    // chunks written by the previous pass
     const int* heads_in;   // [N][blocks of the previous pass] first chunk or -1
@@ -77,7 +78,7 @@ struct TreeArgs {
     int pool_cap;          // chunks in pool_out
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
-    float cell, domega_k, kappa, rcap, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x;
+    float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp;
     float glx[16], glw[16];      // lattice of this pass
     float fx[16], fw[16];        // the render's own lattice (view-term averaging)
 };
@@ -110,7 +111,7 @@ __global__ void tree_tables_kernel(float* sin_t, float* cos_t, float* sin_p, flo
 __global__ void tree_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                   const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N, int B,
                                   float alpha_min, float cell, float level_scale, float level_scale0,
-                                  float alpha_full2, TreeConst* __restrict__ rc, int* __restrict__ status) {
+                                  float alpha_full2, int pixcov, float flat_scale, TreeConst* __restrict__ rc, int* __restrict__ status) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     TreeConst c;
@@ -133,6 +134,15 @@ __global__ void tree_setup_kernel(const float* __restrict__ z6, const float* __r
         c.thr[3] = 1.2f * powf(cell, 8.f / 9.f) * powf(alpha, 1.f / 9.f);
         c.thr[4] = 0.f;
         for (int i = 0; i < TREE_MAX_P; ++i) c.thr[i] = (i == 0 ? level_scale0 : level_scale) * fmaxf(c.thr[i], 6.f * alpha);
+        // ... which assumes that a band's share of the pixel is the tail mass.  A lattice is also accurate wherever the
+        // lobe is flat across the cell: the 2^p-point rule (the 1x1 node with the cell covariance is fourth order like
+        // the 2x2 rule) errs by ~ (cell / sqrt(alpha^2 + d^2))^(2^(p+1)), below 1e-4 beyond c_p cells.  The smaller of
+        // the two distances serves: wide lobes leave the fine lattices early, sharp ones keep the calibrated rule.
+        const float cp[TREE_MAX_P] = {pixcov ? 5.5f : 1e3f, 4.f, 2.6f, 1.7f};
+        for (int i = 0; i < TREE_MAX_P; ++i) {
+            const float flat = sqrtf(fmaxf(cp[i] * cp[i] * cell * cell * flat_scale * flat_scale - c.alpha2, 0.f));
+            c.thr[i] = fminf(c.thr[i], flat);
+        }
     }
     for (int i = 0; i < 3; ++i) c.cdiff[i] = (1.f - c.m) * c.base[i] * (float)M_1_PI;
     c.has_diff = c.cdiff[0] > 0.f || c.cdiff[1] > 0.f || c.cdiff[2] > 0.f;
@@ -255,6 +265,11 @@ __device__ __forceinline__ void texel_diff(const TreeArgs& g, const float* __res
 
 // level `lev` of a pyramid straight from the texels (lev = 1 for the specular pyramid of render blockIdx.y, the base
 // level of the diffuse pyramid of envmap blockIdx.y)
+__global__ void tree_mark_used_kernel(const TreeConst* __restrict__ rc, int N, int* __restrict__ used) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N && rc[k].has_diff) used[rc[k].env] = 1;
+}
+
 template <bool SPEC>
 __global__ void pyr_from_texels_kernel(const TreeArgs g, int lev, float4* __restrict__ pyr) {
     const PyrGeom& G = SPEC ? g.gs : g.gd;
@@ -262,6 +277,7 @@ __global__ void pyr_from_texels_kernel(const TreeArgs g, int lev, float4* __rest
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= Hl * Wl) return;
     const int k = blockIdx.y;
+    if (!SPEC && !g.env_used[k]) return;  // no render of this call reads this envmap's diffuse pyramid
     const int R = cell / Wl, C = cell - R * Wl;
     const int e = 1 << lev;
     const TreeConst* rcp = SPEC ? &g.rc[k] : nullptr;
@@ -302,10 +318,11 @@ __global__ void pyr_from_texels_kernel(const TreeArgs g, int lev, float4* __rest
 }
 
 // level lev from level lev - 1 of every pyramid (blockIdx.y = pyramid)
-__global__ void pyr_merge_kernel(PyrGeom G, int lev, float4* __restrict__ pyr) {
+__global__ void pyr_merge_kernel(PyrGeom G, int lev, float4* __restrict__ pyr, const int* __restrict__ used) {
     const int Hl = G.H[lev], Wl = G.W[lev], Hc = G.H[lev - 1], Wc = G.W[lev - 1];
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= Hl * Wl) return;
+    if (used && !used[blockIdx.y]) return;
     const int R = cell / Wl, C = cell - R * Wl;
     float4* base = pyr + (size_t)blockIdx.y * G.cells * REC4;
     const float4* child = base + G.off[lev - 1] * REC4;
@@ -544,8 +561,11 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         // coarse lattices: it all goes down to the render's own lattice.
         const bool limb = nv_min < fmaxf(g.limb_nv, g.limb_x * sqrtf(rc.alpha2));
         const float thr_p = rc.thr[p] * (limb ? g.limb_boost : 1.f);
-        const float hand_p = limb ? 1e30f : g.hand;
+        const float hand_p = limb ? g.limb_hand : g.hand;
+        const float xthr = g.limb_ramp * sqrtf(rc.alpha2);
         const float alpha2 = rc.alpha2, kappa2 = g.kappa * g.kappa;
+        // wide cells need the second-order terms of G1(n.d) whatever the lobe: without them the cap is half as large
+        const float rcap = rc.full2 ? g.rcap : g.rcap_simple;
 
         // Staged pairs: field f of records 2j, 2j+1 sits at buf1[(j * 26 + f) * 2 + {0,1}].  Fields: 0-2 mu, 3 tr Sigma,
         // 4-6 Sigma_xx,yy,zz, 7-9 2 Sigma_xy,xz,yz, 10 2 v.mu / |mu|^2, 11-13 w RGB, 14-16 m_R, 17-19 m_B,
@@ -553,6 +573,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         const f2 NX = F2(nd.nx), NY = F2(nd.ny), NZ = F2(nd.nz), NV = F2(-nd.nv);
         const f2 Q0 = F2(nd.q0), Q1 = F2(nd.q1), Q2 = F2(nd.q2), Q3 = F2(0.5f * nd.q3), Q4 = F2(0.5f * nd.q4), Q5 = F2(0.5f * nd.q5);
         const f2 CI = F2(rc.inv_a2m1), OMA = F2(rc.one_m_a2), A2 = F2(alpha2);
+        const f2 TRP = F2(nd.P0 + nd.P1 + nd.P2);
         auto eval1 = [&]() {
             if (n1 & 1) {  // pad the last pair with a record of zero weight
                 float* s = buf1 + ((n1 >> 1) * 26) * 2 + 1;
@@ -567,8 +588,12 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     const float4* s = b4 + j * PAIR4;
                     const float4 v0 = s[0], v1 = s[1], v2 = s[2], v3 = s[3], v4 = s[4], v5 = s[5], v6 = s[6], v7 = s[7], v8 = s[8], v9 = s[9];
                     const f2 ex = sub2(NX, lo(v0)), ey = sub2(NY, hi(v0)), ez = sub2(NZ, lo(v1));
-                    const f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
-                    const f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
+                    f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    if (g.pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
+                        u = fma2(TRP, nmu, u);
+                        nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    }
                     f2 nSn = mul2(Q0, lo(v2));
                     nSn = fma2(Q1, hi(v2), nSn); nSn = fma2(Q2, lo(v3), nSn);
                     nSn = fma2(Q3, hi(v3), nSn); nSn = fma2(Q4, lo(v4), nSn); nSn = fma2(Q5, hi(v4), nSn);
@@ -604,8 +629,12 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     const float4 v0 = s[0], v1 = s[1], v2 = s[2], v3 = s[3], v4 = s[4], v5 = s[5], v6 = s[6], v7 = s[7], v8 = s[8], v9 = s[9],
                                  v10 = s[10], v11 = s[11], v12 = s[12];
                     const f2 ex = sub2(NX, lo(v0)), ey = sub2(NY, hi(v0)), ez = sub2(NZ, lo(v1));
-                    const f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
-                    const f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
+                    f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    if (g.pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
+                        u = fma2(TRP, nmu, u);
+                        nmu = fma2(u, F2(-0.5f), F2(1.f));
+                    }
                     f2 nSn = mul2(Q0, lo(v2));
                     nSn = fma2(Q1, hi(v2), nSn); nSn = fma2(Q2, lo(v3), nSn);
                     nSn = fma2(Q3, hi(v3), nSn); nSn = fma2(Q4, lo(v4), nSn); nSn = fma2(Q5, hi(v4), nSn);
@@ -750,7 +779,12 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     // near for this lattice: small cells go to the child blocks, large ones are refined here so that
                     // their far parts stay on this lattice
                     else if (p < g.pk && dmin < thr_p) act = (lev == 0 || rha <= hand_p * thr_p) ? ACT_HAND : ACT_REFINE;
-                    else if (lev > 0 && (rha > g.rcap || rha * rha > kappa2 * (alpha2 + dmin * dmin) ||
+                    // rim blocks: what lies within the shadowing ramp of their horizon goes down as well, in pieces of
+                    // at most 0.05 rad
+                    else if (p < g.pk && limb && spread < 1.5607f &&
+                             adc * __cosf(spread) - sqrtf(fmaxf(1.f - adc * adc, 0.f)) * ss < xthr)
+                        act = (lev == 0 || rha <= 0.05f) ? ACT_HAND : ACT_REFINE;
+                    else if (lev > 0 && (rha > rcap || rha * rha > kappa2 * (alpha2 + dmin * dmin) ||
                                          (2.f * rha > g.hz && fabsf(adc) < ss))) act = ACT_REFINE;
                     else act = ACT_ACCEPT;
                 }
@@ -875,7 +909,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
     tile_writeback(g, red, k, ti, tj, a0, a1, a2, false);
 }
 
-// ---- diffuse lobe: one pass on the 1x1 lattice (the cell's covariance carries the footprint), writes `out` -----------
+// ---- diffuse lobe: one pass, writes `out`.  1x1 lattice whose node carries the covariance of the refmap cell (fourth
+// order in the cell size: cells up to ~0.06 rad), or the render's own lattice for coarser refmaps ------------------------
 __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeArgs g) {
     extern __shared__ __align__(16) unsigned char tree_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -885,7 +920,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeAr
 
     const int k = blockIdx.y;
     const TreeConst rc = g.rc[k];
-    const int tiles_x = (g.res + 15) / 16;
+    const int tiles_x = ((g.res << g.p) + 15) / 16;
     const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
     const int I0 = ti * 16 + (warp >> 1) * 4, J0 = tj * 16 + (warp & 1) * 8;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -1092,6 +1127,7 @@ struct TreeLayout {
     size_t nblocks[TREE_MAX_P];
     int pool_cap[2];
     int* status;
+    int* env_used;
     TreeConst* rc;
     float *sin_t, *cos_t, *sin_p, *cos_p;
     float4 *pyr_s, *pyr_d;
@@ -1115,6 +1151,7 @@ static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We,
     Carver c(ws);
     L.status = c.take<int>(64);
     L.rc = c.take<TreeConst>(N);
+    L.env_used = c.take<int>(B);
     L.sin_t = c.take<float>(He);
     L.cos_t = c.take<float>(He);
     L.sin_p = c.take<float>(We);
@@ -1127,7 +1164,10 @@ static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We,
     for (int p = 0; p < L.pk; ++p) {
         const size_t NG = (size_t)res << p;
         L.nblocks[p] = ((NG + 3) / 4) * ((NG + 7) / 8);
-        const size_t per_block = 4;  // measured: 1.3 chunks per block at the 16x16 footprint (longest list: 26 chunks)
+        // measured chunks per block (worst render of the test set): pass 0: 44 (a wide lobe forced onto a fine lattice
+        // hands most of the map down), 1: 8, 2: 3.7, 3: 1.3; the longest single list was 26 chunks
+        static const size_t budget[TREE_MAX_P] = {64, 24, 10, 6};
+        const size_t per_block = budget[p];
         const size_t n = (size_t)N * L.nblocks[p] * per_block + 64;
         if (n > need[p & 1]) need[p & 1] = n;
         if ((size_t)N * L.nblocks[p] > needh[p & 1]) needh[p & 1] = (size_t)N * L.nblocks[p];
@@ -1187,12 +1227,12 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     TreeArgs g;
     memset(&g, 0, sizeof(g));
     g.env = env; g.rc = L.rc; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
-    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.out = out; g.status = L.status;
+    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.out = out; g.status = L.status; g.env_used = L.env_used;
     g.gs = L.gs; g.gd = L.gd;
     g.B = B; g.He = He; g.We = We; g.N = N; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
-    g.kappa = o.kappa; g.rcap = o.rcap; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x;
+    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp;
     gauss_legendre_t(S, g.fx, g.fw);
 
     const int tb = 128;
@@ -1203,8 +1243,10 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     const float grow = (float)fmin(10.0, pow(fmax(1.0, (M_PI / res) / (M_PI / 128.0)), 1.5));
     tree_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell,
                                                        o.level_scale * grow, (o.pixel_covariance ? o.level_scale0 : o.level_scale) * grow,
-                                                       o.full_second_order ? o.alpha_full2 : 1e30f, L.rc, L.status);
-    count_launches(2);
+                                                       o.full_second_order ? o.alpha_full2 : 1e30f, o.pixel_covariance, o.flat_scale, L.rc, L.status);
+    DRM_CHECK_CUDA(cudaMemsetAsync(L.env_used, 0, sizeof(int) * B, st));
+    tree_mark_used_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(L.rc, N, L.env_used);
+    count_launches(3);
     // ---- pyramids --------------------------------------------------------------------------------------------------
     if (L.gs.L >= 1) {
         const int n1 = L.gs.H[1] * L.gs.W[1];
@@ -1212,7 +1254,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
         count_launches(1);
         for (int l = 2; l <= L.gs.L; ++l) {
             const int nl = L.gs.H[l] * L.gs.W[l];
-            pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, N), tb, 0, st>>>(L.gs, l, L.pyr_s);
+            pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, N), tb, 0, st>>>(L.gs, l, L.pyr_s, nullptr);
             count_launches(1);
         }
     }
@@ -1223,7 +1265,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
         count_launches(1);
         for (int l = first + 1; l <= L.gd.L; ++l) {
             const int nl = L.gd.H[l] * L.gd.W[l];
-            pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, B), tb, 0, st>>>(L.gd, l, L.pyr_d);
+            pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, B), tb, 0, st>>>(L.gd, l, L.pyr_d, L.env_used);
             count_launches(1);
         }
     }
@@ -1232,10 +1274,12 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     DRM_CHECK_CUDA(cudaFuncSetAttribute(tree_spec_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM));
     {
         TreeArgs a = g;
-        a.p = 0;
-        a.pixcov = (o.pixel_covariance && L.pk > 0) ? 1 : 0;
-        gauss_legendre_t(1, a.glx, a.glw);
-        const int tiles = ((res + 15) / 16) * ((res + 15) / 16);
+        const bool cov = o.pixel_covariance && L.pk > 0 && g.cell <= 0.06f;
+        a.p = (L.pk > 0 && !cov) ? L.pk : 0;
+        a.pixcov = cov ? 1 : 0;
+        gauss_legendre_t(1 << a.p, a.glx, a.glw);
+        const int NGd = res << a.p;
+        const int tiles = ((NGd + 15) / 16) * ((NGd + 15) / 16);
         tree_diff_kernel<<<dim3(tiles, N), TREE_THREADS, TREE_SMEM, st>>>(a);
         count_launches(1);
     }
@@ -1270,17 +1314,21 @@ extern "C" int drm_render_refmaps(const float* env, int B, int He, int We, const
 extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     if (!o) return;
     o->kappa = 0.1f;
-    o->rcap = 0.03f;
+    o->rcap = 0.06f;
+    o->rcap_simple = 0.025f;
     o->horizon = 0.03f;
-    o->kappa_diffuse = 0.05f;
+    o->kappa_diffuse = 0.1f;
     o->horizon_diffuse = 0.03f;
     o->level_scale = 0.6f;
     o->level_scale0 = 0.6f;
     o->pixel_covariance = 1;
     o->full_second_order = 1;
-    o->alpha_full2 = 0.2f;
+    o->alpha_full2 = 0.1f;
     o->hand_over = 0.5f;
     o->limb_nv = 0.0f;
     o->limb_boost = 2.f;
     o->limb_x = 8.f;
+    o->flat_scale = 1.4f;
+    o->limb_hand = 1e30f;
+    o->limb_ramp = 0.f;
 }

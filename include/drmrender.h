@@ -66,7 +66,8 @@ int drm_render_refmaps(const float* env, int B, int He, int We,
 typedef struct DrmRenderOptions {
     float kappa;            /* a pyramid cell of half-vector radius r serves a block of normals at distance d when
                                r <= kappa * sqrt(alpha^2 + d^2) ... */
-    float rcap;             /* ... and r <= rcap (radians) */
+    float rcap;             /* ... and r <= rcap (radians) for renders evaluated with the full second-order terms, */
+    float rcap_simple;      /* r <= rcap_simple for the others (alpha < alpha_full2) */
     float horizon;          /* cells wider than this (radians) are refined where they straddle the horizon n.d = 0 */
     float kappa_diffuse;    /* diffuse lobe: largest cell radius (radians) */
     float horizon_diffuse;  /* diffuse lobe: the same horizon rule */
@@ -79,7 +80,12 @@ typedef struct DrmRenderOptions {
                                hand_over * (that lattice's distance); larger cells are refined first */
     float limb_nv;          /* blocks of normals with min n.v below max(limb_nv, limb_x * alpha) ... */
     float limb_boost;       /* ... use lattice distances scaled by this (the cell average converges later at the limb) ... */
-    float limb_x;           /* ... and hand everything that comes near down to the render's own lattice */
+    float limb_x;           /* ... (the rim of the refmap) ... */
+    float limb_hand;        /* hand_over of the rim blocks (default: unbounded, every near cell goes down whole) */
+    float limb_ramp;        /* rim blocks also hand down what lies within limb_ramp * alpha of their horizon n.d = 0
+                               (default 0: off; with a finite limb_hand this is cheaper and accurate to ~3e-3 locally) */
+    float flat_scale;       /* scale of the distances (in cells) beyond which a lattice is accurate because the lobe is
+                               flat across the cell */
 } DrmRenderOptions;
 
 void drm_render_default_options(DrmRenderOptions* opts);

@@ -109,9 +109,67 @@ def synthetic_envmap(He, We, seed):
     return gen(He, We, seed)
 
 
+def smooth_mirmap_golden():
+    """Mirror-limit known answer on a SMOOTH map (three broad lobes + a floor): the reference's envmap2mirmap output for
+    two views.  tests/test_oracle_brdf_pins.py renders z0 on a super-sampled copy of this map and compares at 1e-2."""
+    He, We = 64, 128
+    t = (np.arange(He) + 0.5) * np.pi / He
+    p = (np.arange(We) + 0.5) * 2 * np.pi / We
+    st, ct = np.sin(t)[:, None], np.cos(t)[:, None]
+    d = np.stack([st * np.sin(p)[None], np.broadcast_to(ct, (He, We)), -st * np.cos(p)[None]], -1)
+    env = np.zeros((He, We, 3))
+    for k, amp, col in (((0.3, 0.5, 0.8), 3.0, (1, .8, .6)), ((-0.7, 0.2, -0.4), 2.0, (.5, .9, 1.0)),
+                        ((0.1, -0.8, 0.5), 1.5, (.9, .9, .4))):
+        k = np.array(k) / np.linalg.norm(k)
+        env += amp * np.exp(4.0 * (d @ k - 1))[..., None] * np.array(col)
+    env = (env + 0.2).astype(np.float32)
+    env_t = torch.from_numpy(env).permute(2, 0, 1)[None]
+    blob = {"env": env}
+    for tag, view in {"v001": [0.0, 0.0, 1.0], "vdiag": [0.6, 0.0, 0.8]}.items():
+        blob[f"mirmap_{tag}"] = envmap2mirmap(env_t, (32, 32), view_from=view)[0].permute(1, 2, 0).numpy()
+        blob[f"view_{tag}"] = np.asarray(view, np.float32)
+    np.savez_compressed(OUT / "mirmap_smooth.npz", **blob)
+
+
+def callers_golden():
+    """Known answers for the steps either side of the render, produced by the reference's own code:
+    * dataset/basedataset.py BaseDataset.transform for `log` and for ObsNet's
+      `0p1tom1p1_normalizedLogarithmic_lowerbound1e-6` with dynamic normalisation under a mask (:52-76), imported;
+    * the luminance normalisation of DRMNet.get_input (models/drmnet.py:610-617): models/drmnet.py cannot be imported
+      here (mitsuba, pytorch_lightning), so exactly those source lines are read from the reference file and executed."""
+    import textwrap
+    import types
+    from dataset.basedataset import BaseDataset
+    g = torch.Generator().manual_seed(11)
+    x = torch.exp(1.5 * torch.randn(3, 4, 3, 16, 16, generator=g))  # [G, N, 3, res, res]
+    x[0, 1, :, :4] = 0.0  # zero-luminance pixels are left out of the geometric mean
+    ds = BaseDataset(size=16, transform_func="log")
+    src = (REF / "models" / "drmnet.py").read_text().splitlines()[609:617]
+    assert src[0].strip().startswith("if self.refmap_input_scaler is not None:") and "stacked_Lr[idx] = Lr" in src[-1], src
+    ns = {"torch": torch, "self": types.SimpleNamespace(refmap_input_scaler=0.12), "stacked_Lr": [t.clone() for t in x]}
+    exec(textwrap.dedent("\n".join(src)), ns)
+    scaled = torch.stack(ns["stacked_Lr"])
+    out = torch.stack([ds.transform(t) for t in scaled])
+    blob = {"post_in": x.numpy(), "post_scale": ns["self"].normalizing_scale.numpy(), "post_out": out.numpy()}
+    ds2 = BaseDataset(size=16, transform_func="0p1tom1p1_normalizedLogarithmic_lowerbound1e-6")
+    y = torch.exp(2.0 * torch.randn(4, 3, 16, 16, generator=g))
+    y[0, :, 0, 0] = 0.0  # below the lower bound
+    mask = (torch.rand(4, 1, 16, 16, generator=g) > 0.3)
+    blob["nlog_in"] = y.numpy()
+    blob["nlog_mask"] = mask.numpy()
+    blob["nlog_out"] = ds2.transform(y, dynamic_normalize=True, mask=mask).numpy()
+    blob["nlog_min"] = ds2.Logarithmic_params[0].reshape(-1).numpy()
+    blob["nlog_max"] = ds2.Logarithmic_params[1].reshape(-1).numpy()
+    np.savez_compressed(OUT / "callers_ref.npz", **blob)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    smooth_mirmap_golden()
+    callers_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "small":  # only the two quick files above
+        return
 
     colors, normals = sample_inputs()
     refmap, refmask = refmap_mask_make(colors, normals, 128, np.pi / 128 / 2)

@@ -71,6 +71,20 @@ static double smith_g1(double c, double alpha) {
     return 2.0 / (1.0 + sqrt(1.0 + t2));
 }
 
+static double ggx_d(double nh, double alpha) {
+    /* D = 1 / (pi alpha^2 (cos^2 + sin^2 / alpha^2)^2) */
+    double c2 = nh * nh;
+    double q = c2 + (1.0 - c2) / (alpha * alpha);
+    return 1.0 / (M_PI * alpha * alpha * q * q);
+}
+
+/* the BSDF building blocks, exported so that tests can check their identities by independent quadrature
+   (microfacet normalisation, weak white furnace, F0 = 0.08 specular) */
+double drm_oracle_ggx_d(double nh, double alpha) { return ggx_d(nh, alpha); }
+double drm_oracle_smith_g1(double c, double alpha) { return smith_g1(c, alpha); }
+double drm_oracle_fresnel_dielectric(double cos_i, double eta) { return fresnel_dielectric(cos_i, eta); }
+double drm_oracle_eta_from_specular(double specular) { return 2.0 / (1.0 - sqrt(0.08 * specular)) - 1.0; }
+
 /* camera frame of look_at(origin = v, target = 0, up = (0,1,0)) */
 static void camera_frame(const double* view, double* vhat, double* left, double* upp) {
     double len = sqrt(view[0] * view[0] + view[1] * view[1] + view[2] * view[2]);
@@ -135,11 +149,10 @@ static void render_cell(int i, int j, const double* rec_dir, const double* rec_E
                 const double* E = rec_E + 3 * t;
                 if (terms & 1) {
                     double nh = (nv + nd) * p[0];
-                    double c2 = nh * nh;
-                    double q = c2 + (1.0 - c2) / (alpha * alpha);
-                    double D = 1.0 / (M_PI * alpha * alpha * q * q);
+                    double D = ggx_d(nh, alpha);
                     if (D * nh <= 1e-20) D = 0.0;
-                    double w = D * g1v * smith_g1(nd, alpha) / (4.0 * nv);
+                    /* terms bit 2 (tests only): leave G1(n.d) out -- the weak white furnace integrand */
+                    double w = D * g1v * ((terms & 4) ? 1.0 : smith_g1(nd, alpha)) / (4.0 * nv);
                     s_acc[0] += w * p[2] * E[0];
                     s_acc[1] += w * p[3] * E[1];
                     s_acc[2] += w * p[4] * E[2];
@@ -162,7 +175,7 @@ static void render_cell(int i, int j, const double* rec_dir, const double* rec_E
 /*
  * z6 = [metallic, base R, base G, base B, roughness, specular] (already clipped to [0,1]).
  * gl_x / gl_w: S Gauss-Legendre nodes on [-1,1] and weights normalised to sum 1.
- * terms: bit 0 = specular, bit 1 = diffuse.
+ * terms: bit 0 = specular, bit 1 = diffuse, bit 2 = specular without the shadowing factor G1(n.d) (tests only).
  * window: NULL, or {i0, i1, j0, j1}: only cells i0 <= i < i1, j0 <= j < j1 are evaluated (the rest of out stays 0).
  * out: [res, res, 3] doubles.
  */

@@ -48,6 +48,10 @@ def _load():
                                                  ctypes.POINTER(ctypes.c_int), ctypes.c_int, dp]
         _lib.drm_oracle_render_cells.restype = ctypes.c_int
         _lib.drm_oracle_num_threads.restype = ctypes.c_int
+        for fn, n in (('drm_oracle_ggx_d', 2), ('drm_oracle_smith_g1', 2), ('drm_oracle_fresnel_dielectric', 2),
+                      ('drm_oracle_eta_from_specular', 1)):
+            getattr(_lib, fn).restype = ctypes.c_double
+            getattr(_lib, fn).argtypes = [ctypes.c_double] * n
     return _lib
 
 
@@ -160,6 +164,13 @@ def render_oracle_cells(env, z, view, res, cells, *, names=None, S=1, flip=False
     if rc != 0:
         raise MemoryError("render oracle allocation failed")
     return out
+
+
+def bsdf_blocks():
+    """(D(n.h, alpha), G1(c, alpha), F_dielectric(cos, eta), eta(specular)) of the C restatement as Python callables."""
+    lib = _load()
+    return (lib.drm_oracle_ggx_d, lib.drm_oracle_smith_g1, lib.drm_oracle_fresnel_dielectric,
+            lib.drm_oracle_eta_from_specular)
 
 
 def rel_l2(a, b) -> float:

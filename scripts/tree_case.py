@@ -23,11 +23,12 @@ for i in [int(x) for x in sys.argv[2:]]:
         got = out[cl[:, 0], cl[:, 1]]
         e = np.abs(got - ref).max(1); k = int(e.argmax())
         print(f"  {name:28s} rel-L2 {np.linalg.norm(got-ref)/np.linalg.norm(ref):.2e} max/peak {e.max()/np.abs(ref).max():.2e} at cell {cl[k]} marks {getattr(render_batch,'last_status',None)}")
-    run("flat", flat=True)
     run("default")
-    run("level_scale x2", level_scale=0.6, level_scale0=0.3)
-    run("level_scale x3", level_scale=0.9, level_scale0=0.45)
-    run("ls x2, no limb", level_scale=0.6, level_scale0=0.3, limb_boost=1.0)
-    run("hand 1e6", hand_over=1e6)
-    run("kappa 0.05", kappa=0.05)
+    run("flat", flat=True)
+    run("kappa .07", kappa=0.07)
+    run("alpha_full2 .1", alpha_full2=0.1)
+    run("flat_scale 2.5", flat_scale=2.5)
     run("no pixcov", pixel_covariance=0)
+    run("ls 1.2", level_scale=1.2, level_scale0=1.2)
+    run("hz .015", horizon=0.015)
+    run("rcap .03", rcap=0.03)

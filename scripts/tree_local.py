@@ -28,8 +28,9 @@ for i in [int(x) for x in sys.argv[2:]]:
         k = np.unravel_index(loc.argmax(), loc.shape)
         print(f"  {name:34s} rel-L2 {np.linalg.norm(a-b)/np.linalg.norm(b):.2e} local max {loc.max():.2e} at {k} p99.9 {np.quantile(loc,0.999):.2e}  {e0.elapsed_time(e1):.2f} ms")
     run("default")
-    run("limb_x 3", limb_x=3.0)
-    run("limb_x 12", limb_x=12.0)
-    run("limb off", limb_x=0.0)
-    run("ls .3", level_scale=0.3, level_scale0=0.3)
-    run("ls .6", level_scale=0.6, level_scale0=0.6)
+    run("limb_hand inf ramp 0 (old)", limb_hand=1e30, limb_ramp=0.0)
+    run("limb_hand 1", limb_hand=1.0)
+    run("limb_hand 4", limb_hand=4.0)
+    run("ramp 3", limb_ramp=3.0)
+    run("ramp 12", limb_ramp=12.0)
+    run("limb_hand .5 ramp 0 (= limb off)", limb_hand=0.5, limb_ramp=0.0)

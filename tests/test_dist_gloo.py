@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from drmnet_b200.dist import all_gather_refmaps, owned_envmaps, shard_renders
+from drmnet_b200.dist import RefmapGather, all_gather_refmaps, owned_envmaps, shard_by_cost, shard_renders
 
 
 def _free_port():
@@ -32,6 +32,19 @@ def _worker(rank, world, port, total, n_env, result_dir):
         full = all_gather_refmaps(local, mine, total)
         expect = torch.arange(total, dtype=torch.float32)[:, None, None, None].expand(total, 3, 4, 4)
         assert torch.equal(full, expect)
+        # the fixed-count path bench.py uses: every rank knows every rank's ids, one collective, no count exchange
+        ids_per_rank = [shard_renders(env_index, world, r)[0] for r in range(world)]
+        g = RefmapGather(ids_per_rank, total, "cpu")
+        g.launch(local)
+        assert torch.equal(g.result(), expect)
+        # cost-balanced sharding: a partition of the renders, the same on every rank
+        cost = torch.rand(total, generator=torch.Generator().manual_seed(1)) ** 4
+        parts = shard_by_cost(cost, world)
+        assert sorted(int(i) for p in parts for i in p) == list(range(total))
+        local2 = torch.stack([torch.full((3, 4, 4), float(i)) for i in parts[rank]]) if len(parts[rank]) else torch.zeros(0, 3, 4, 4)
+        g2 = RefmapGather(parts, total, "cpu")
+        g2.launch(local2)
+        assert torch.equal(g2.result(), expect)
         torch.save(full, os.path.join(result_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -55,3 +68,12 @@ def test_ownership_partition():
     for world in (1, 2, 4, 8):
         seen = sorted(b for r in range(world) for b in owned_envmaps(13, world, r))
         assert seen == list(range(13))
+
+
+def test_cost_balanced_sharding_is_balanced():
+    cost = torch.tensor([16.0] * 4 + [4.0] * 8 + [1.0] * 52)  # a footprint mix: a few expensive renders
+    for world in (2, 4, 8):
+        parts = shard_by_cost(cost, world)
+        loads = [float(cost[p].sum()) for p in parts]
+        assert sorted(int(i) for p in parts for i in p) == list(range(64))
+        assert max(loads) - min(loads) <= 16.0 and max(loads) <= 1.15 * sum(loads) / world + 1e-9

@@ -14,6 +14,28 @@ def test_mirmap2envmap_oracle_matches_reference_output(golden_mirmap):
     assert np.abs(ours - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
+
+def test_postprocess_oracle_matches_reference_code():
+    """golden (oracle/gen_golden.py callers_golden): the source lines models/drmnet.py:610-617 executed as they stand,
+    then the reference's BaseDataset('log').transform (dataset/basedataset.py:52-53)."""
+    g = np.load(GOLDEN / "callers_ref.npz")
+    ours, s = postprocess_oracle(g["post_in"])
+    assert np.allclose(s, g["post_scale"], rtol=2e-6)
+    assert np.allclose(ours, g["post_out"], rtol=2e-6, atol=2e-6)
+
+
+def test_normalized_log_oracle_matches_reference_code():
+    """golden: the reference's BaseDataset('0p1tom1p1_normalizedLogarithmic_lowerbound1e-6').transform with
+    dynamic_normalize=True under a mask (dataset/basedataset.py:56-76), imported and run."""
+    from oracle.callers_oracle import normalized_log_oracle
+    g = np.load(GOLDEN / "callers_ref.npz")
+    ours, lmin, lmax = normalized_log_oracle(g["nlog_in"], g["nlog_mask"])
+    assert np.allclose(ours, g["nlog_out"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(lmin, g["nlog_min"], atol=1e-6) and np.allclose(lmax, g["nlog_max"], atol=1e-6)
+
+
 def test_postprocess_oracle_matches_torch_formulas():
     """The same expressions evaluated with torch ops (models/drmnet.py:610-620, dataset/basedataset.py:52-53)."""
     g = torch.Generator().manual_seed(0)
