@@ -78,7 +78,7 @@ struct TreeArgs {
     int pool_cap;          // chunks in pool_out
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
-    float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp;
+    float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub;
     float glx[16], glw[16];      // lattice of this pass
     float fx[16], fw[16];        // the render's own lattice (view-term averaging)
 };
@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         // zero the view factor and the shadowing ramp G1(n.d) vary across the cell however far the half vector is: blocks
         // that touch this rim (the outermost cells of the refmap for a sharp lobe) accept nothing that comes near on the
         // coarse lattices: it all goes down to the render's own lattice.
-        const bool limb = nv_min < fmaxf(g.limb_nv, g.limb_x * sqrtf(rc.alpha2));
+        // (a lattice whose sub-cells are narrower than limb_sub * alpha resolves that ramp: no rim rule on it)
+        const float subw = g.cell / (float)(1 << p);
+        const bool limb = nv_min < fmaxf(g.limb_nv, g.limb_x * sqrtf(rc.alpha2)) && subw * subw > g.limb_sub * g.limb_sub * rc.alpha2;
         const float thr_p = rc.thr[p] * (limb ? g.limb_boost : 1.f);
         const float hand_p = limb ? g.limb_hand : g.hand;
         const float xthr = g.limb_ramp * sqrtf(rc.alpha2);
@@ -1232,7 +1234,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     g.B = B; g.He = He; g.We = We; g.N = N; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
-    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp;
+    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub;
     gauss_legendre_t(S, g.fx, g.fw);
 
     const int tb = 128;
@@ -1329,6 +1331,7 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->limb_boost = 2.f;
     o->limb_x = 8.f;
     o->flat_scale = 1.4f;
+    o->limb_sub = 0.f;
     o->limb_hand = 1e30f;
     o->limb_ramp = 0.f;
 }

@@ -81,6 +81,7 @@ typedef struct DrmRenderOptions {
     float limb_nv;          /* blocks of normals with min n.v below max(limb_nv, limb_x * alpha) ... */
     float limb_boost;       /* ... use lattice distances scaled by this (the cell average converges later at the limb) ... */
     float limb_x;           /* ... (the rim of the refmap) ... */
+    float limb_sub;         /* ... on the lattices whose sub-cells are wider than limb_sub * alpha ... */
     float limb_hand;        /* hand_over of the rim blocks (default: unbounded, every near cell goes down whole) */
     float limb_ramp;        /* rim blocks also hand down what lies within limb_ramp * alpha of their horizon n.d = 0
                                (default 0: off; with a finite limb_hand this is cheaper and accurate to ~3e-3 locally) */
