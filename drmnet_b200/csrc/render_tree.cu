@@ -58,6 +58,7 @@ struct TreeConst {  // per render
     float base[3], cdiff[3];
     float thr[TREE_MAX_P + 1];  // half-vector-space distance beyond which lattice 2^p resolves the cell average
     int env, has_spec, has_diff, full2;
+    int pk, pad[3];  // log2 of the render's footprint S
 };
 
 struct TreeArgs {
@@ -79,8 +80,8 @@ struct TreeArgs {
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
     float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub;
-    float glx[16], glw[16];      // lattice of this pass
-    float fx[16], fw[16];        // the render's own lattice (view-term averaging)
+    float glx[TREE_MAX_P + 1][16], glw[TREE_MAX_P + 1][16];  // Gauss-Legendre lattices 1, 2, 4, 8, 16
+    int diff_cov;                // diffuse pass: 1x1 lattice with the cell covariance (else the render's own lattice)
 };
 
 __device__ __forceinline__ float fresnel_dielectric_t(float cos_i, float eta) {
@@ -111,7 +112,8 @@ __global__ void tree_tables_kernel(float* sin_t, float* cos_t, float* sin_p, flo
 __global__ void tree_setup_kernel(const float* __restrict__ z6, const float* __restrict__ view3,
                                   const uint8_t* __restrict__ flip, const int32_t* __restrict__ env_index, int N, int B,
                                   float alpha_min, float cell, float level_scale, float level_scale0,
-                                  float alpha_full2, int pixcov, float flat_scale, TreeConst* __restrict__ rc, int* __restrict__ status) {
+                                  float alpha_full2, int pixcov, float flat_scale, int S_uniform, const int32_t* __restrict__ S_per_render,
+                                  TreeConst* __restrict__ rc, int* __restrict__ status) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     TreeConst c;
@@ -165,6 +167,20 @@ __global__ void tree_setup_kernel(const float* __restrict__ z6, const float* __r
     if (e < 0 || e >= B) atomicOr(status, 2);  // reported by drm_render_status; the render uses a clamped index
     c.env = min(max(e, 0), B - 1);
     c.full2 = alpha >= alpha_full2;
+    {
+        // footprint: given per render, given for the call, or chosen from the ratio of cell width to lobe half-width
+        // (the rule of renderer.auto_footprint: the cell average of the lobe resolved to ~2e-4)
+        int S = S_per_render ? S_per_render[k] : S_uniform;
+        if (S <= 0) {
+            const float ratio = cell / alpha;
+            S = ratio < 0.1f ? 1 : ratio < 0.6f ? 2 : ratio < 2.f ? 4 : ratio < 4.f ? 8 : 16;
+        }
+        int pk = 0;
+        while ((1 << pk) < S && pk < TREE_MAX_P) ++pk;
+        if ((1 << pk) != S) atomicOr(status, 8);  // not one of 1, 2, 4, 8, 16: rounded up, reported
+        c.pk = pk;
+        c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    }
     rc[k] = c;
 }
 
@@ -373,22 +389,27 @@ struct NodeT {
     bool active;
 };
 
-__device__ __forceinline__ void make_node(const TreeArgs& g, const TreeConst& rc, int I, int J, bool spec, NodeT& nd) {
-    const int p = g.p, Sk = 1 << p, S = 1 << g.pk;
+__device__ __forceinline__ void make_node(const TreeArgs& g, const TreeConst& rc, int p, bool pixcov, int I, int J, bool spec,
+                                          NodeT& nd) {
+    const int pk = rc.pk, Sk = 1 << p, S = 1 << pk;
+    const float* __restrict__ glx = g.glx[p];
+    const float* __restrict__ glw = g.glw[p];
+    const float* __restrict__ fx = g.glx[pk];
+    const float* __restrict__ fw = g.glw[pk];
     const int NG = g.res << p;
     nd.active = I < NG && J < NG;
     const int i = I >> p, a = I & (Sk - 1), j = J >> p, b = J & (Sk - 1);
     float sa = 0.f, sb = 0.f, meanv = -1.f;
-    if (spec && p < g.pk && nd.active) {
+    if (spec && p < pk && nd.active) {
         const int m = S / Sk;
         float num = 0.f, den = 0.f, va = 0.f, vb = 0.f, ua = 0.f, ub = 0.f;
         for (int ia = 0; ia < m; ++ia) {
-            const float xa = g.fx[a * m + ia], wa = g.fw[a * m + ia];
+            const float xa = fx[a * m + ia], wa = fw[a * m + ia];
             const float st = sinf(((float)i + 0.5f + 0.5f * xa) * g.cell);
             for (int ib = 0; ib < m; ++ib) {
-                const float xb = g.fx[b * m + ib];
+                const float xb = fx[b * m + ib];
                 const float sp = sinf(((float)j + 0.5f + 0.5f * xb) * g.cell);
-                const float w = wa * g.fw[b * m + ib];
+                const float w = wa * fw[b * m + ib];
                 const float wv = w * view_term_t(rc, st * sp);
                 num += wv; den += w;
                 va += wv * xa; vb += wv * xb;
@@ -398,8 +419,8 @@ __device__ __forceinline__ void make_node(const TreeArgs& g, const TreeConst& rc
         if (num > 0.f) { meanv = num / den; sa = va / num - ua / den; sb = vb / num - ub / den; }
         else meanv = 0.f;
     }
-    const float th = ((float)i + 0.5f + 0.5f * (g.glx[a] + sa)) * g.cell;
-    const float ph = ((float)j + 0.5f + 0.5f * (g.glx[b] + sb)) * g.cell;
+    const float th = ((float)i + 0.5f + 0.5f * (glx[a] + sa)) * g.cell;
+    const float ph = ((float)j + 0.5f + 0.5f * (glx[b] + sb)) * g.cell;
     float st, ct, sp, cp;
     sincosf(th, &st, &ct);
     sincosf(ph, &sp, &cp);
@@ -408,14 +429,14 @@ __device__ __forceinline__ void make_node(const TreeArgs& g, const TreeConst& rc
     nd.ny = lx * rc.left[1] + ct * rc.upp[1] + lz * rc.vhat[1];
     nd.nz = lx * rc.left[2] + ct * rc.upp[2] + lz * rc.vhat[2];
     nd.nv = lz;  // n . v exactly, the frame is orthonormal
-    nd.wq = nd.active ? g.glw[a] * g.glw[b] : 0.f;
+    nd.wq = nd.active ? glw[a] * glw[b] : 0.f;
     nd.mult = nd.wq * (meanv >= 0.f ? meanv : view_term_t(rc, lz));
     const float mm = fminf(fmaxf(1.f - lz, 0.f), 1.f);
     nd.Fi = (mm * mm) * (mm * mm) * mm;
     nd.q0 = nd.nx * nd.nx; nd.q1 = nd.ny * nd.ny; nd.q2 = nd.nz * nd.nz;
     nd.q3 = 2.f * nd.nx * nd.ny; nd.q4 = 2.f * nd.nx * nd.nz; nd.q5 = 2.f * nd.ny * nd.nz;
     nd.P0 = nd.P1 = nd.P2 = nd.P3 = nd.P4 = nd.P5 = 0.f;
-    if (g.pixcov && p == 0 && g.pk > 0) {
+    if (pixcov) {
         // uniform box in (theta, phi) of width cell: covariance (cell^2 / 12)(e_t e_t^T + e_p e_p^T), e = dn/dtheta, dn/dphi
         const float var = g.cell * g.cell * (1.f / 12.f);
         const float lxt = ct * cp, lzt = ct * sp, lxp = -st * sp, lzp = st * cp;
@@ -459,7 +480,7 @@ __device__ __forceinline__ float fast_radius_angle(float c) {
 }
 
 // cone (axis, half angle) of the warp's active nodes, widened by the sub-cells the nodes stand for
-__device__ __forceinline__ bool warp_cone(const TreeArgs& g, const NodeT& nd, float& ax, float& ay, float& az, float& beta) {
+__device__ __forceinline__ bool warp_cone(const TreeArgs& g, int p, const NodeT& nd, float& ax, float& ay, float& az, float& beta) {
     const float wa = nd.active ? 1.f : 0.f;
     ax = warp_sum(wa * nd.nx); ay = warp_sum(wa * nd.ny); az = warp_sum(wa * nd.nz);
     const float cnt = warp_sum(wa);
@@ -467,7 +488,7 @@ __device__ __forceinline__ bool warp_cone(const TreeArgs& g, const NodeT& nd, fl
     const float inv = rsqrtf(fmaxf(ax * ax + ay * ay + az * az, 1e-30f));
     ax *= inv; ay *= inv; az *= inv;
     const float dx = nd.nx - ax, dy = nd.ny - ay, dz = nd.nz - az;
-    beta = warp_max(nd.active ? chord_angle(dx * dx + dy * dy + dz * dz) : 0.f) + 0.75f * g.cell / (float)(1 << g.p);
+    beta = warp_max(nd.active ? chord_angle(dx * dx + dy * dy + dz * dz) : 0.f) + 0.75f * g.cell / (float)(1 << p);
     return true;
 }
 
@@ -488,13 +509,13 @@ __device__ __forceinline__ f2 lo(float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ f2 hi(float4 v) { return make_float2(v.z, v.w); }
 
 // add the per-node sums to the cells of the CTA's 16 x 16 node tile, in fixed order (deterministic)
-__device__ __forceinline__ void tile_writeback(const TreeArgs& g, float* red, int k, int ti, int tj, float a0, float a1, float a2,
-                                               bool overwrite) {
+__device__ __forceinline__ void tile_writeback(const TreeArgs& g, int p, float* red, int k, int ti, int tj, float a0, float a1,
+                                               float a2, bool overwrite) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ln = ((warp >> 1) * 4 + (lane >> 3)) * 16 + (warp & 1) * 8 + (lane & 7);  // node (row, col) inside the tile
     red[ln * 3 + 0] = a0; red[ln * 3 + 1] = a1; red[ln * 3 + 2] = a2;
     __syncthreads();
-    const int p = g.p, Sk = 1 << p, cpt = 16 >> p;  // cells per tile edge
+    const int Sk = 1 << p, cpt = 16 >> p;  // cells per tile edge
     if (cpt < 1) return;
     const int ncell = cpt * cpt;
     for (int o = tid; o < ncell * 3; o += TREE_THREADS) {
@@ -522,17 +543,19 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
 
     const int k = blockIdx.y;
     const TreeConst rc = g.rc[k];
-    const int p = g.p;
+    const int p = g.p, pk = rc.pk;
+    if (p > pk) return;  // this render's own lattice is coarser: its last pass has run (uniform over the CTA)
     const int NG = g.res << p;
     const int tiles_x = (NG + 15) / 16;
     const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
     const int I0 = ti * 16 + (warp >> 1) * 4, J0 = tj * 16 + (warp & 1) * 8;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const bool pixcov = g.pixcov && p == 0 && pk > 0;  // the 1x1 node of a finer footprint carries the cell's covariance
 
     NodeT nd;
-    make_node(g, rc, I0 + (lane >> 3), J0 + (lane & 7), true, nd);
+    make_node(g, rc, p, pixcov, I0 + (lane >> 3), J0 + (lane & 7), true, nd);
     float ax, ay, az, beta;
-    const bool live = rc.has_spec && warp_cone(g, nd, ax, ay, az, beta);
+    const bool live = rc.has_spec && warp_cone(g, p, nd, ax, ay, az, beta);
 
     if (live) {
         const float4* pyr = g.pyr_s + (size_t)k * g.gs.cells * REC4;
@@ -592,14 +615,14 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     const f2 ex = sub2(NX, lo(v0)), ey = sub2(NY, hi(v0)), ez = sub2(NZ, lo(v1));
                     f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
                     f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
-                    if (g.pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
+                    if (pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
                         u = fma2(TRP, nmu, u);
                         nmu = fma2(u, F2(-0.5f), F2(1.f));
                     }
                     f2 nSn = mul2(Q0, lo(v2));
                     nSn = fma2(Q1, hi(v2), nSn); nSn = fma2(Q2, lo(v3), nSn);
                     nSn = fma2(Q3, hi(v3), nSn); nSn = fma2(Q4, lo(v4), nSn); nSn = fma2(Q5, hi(v4), nSn);
-                    if (g.pixcov) {
+                    if (pixcov) {
                         const f2 mx = lo(v0), my = hi(v0), mz = lo(v1);
                         f2 pp = mul2(mul2(mx, mx), F2(nd.P0));
                         pp = fma2(mul2(my, my), F2(nd.P1), pp); pp = fma2(mul2(mz, mz), F2(nd.P2), pp);
@@ -633,7 +656,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     const f2 ex = sub2(NX, lo(v0)), ey = sub2(NY, hi(v0)), ez = sub2(NZ, lo(v1));
                     f2 u = fma2(ez, ez, fma2(ey, ey, fma2(ex, ex, hi(v1))));
                     f2 nmu = fma2(u, F2(-0.5f), F2(1.f));
-                    if (g.pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
+                    if (pixcov) {  // the normal's spread over the cell also moves the mean of 2 - 2 n.h: + tr P (n.h)
                         u = fma2(TRP, nmu, u);
                         nmu = fma2(u, F2(-0.5f), F2(1.f));
                     }
@@ -641,7 +664,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     nSn = fma2(Q1, hi(v2), nSn); nSn = fma2(Q2, lo(v3), nSn);
                     nSn = fma2(Q3, hi(v3), nSn); nSn = fma2(Q4, lo(v4), nSn); nSn = fma2(Q5, hi(v4), nSn);
                     f2 pS = nSn;
-                    if (g.pixcov) {
+                    if (pixcov) {
                         const f2 mx = lo(v0), my = hi(v0), mz = lo(v1);
                         f2 pp = mul2(mul2(mx, mx), F2(nd.P0));
                         pp = fma2(mul2(my, my), F2(nd.P1), pp); pp = fma2(mul2(mz, mz), F2(nd.P2), pp);
@@ -780,10 +803,10 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                     if (spread < 1.5607f && adc <= -ss) act = ACT_DROP;
                     // near for this lattice: small cells go to the child blocks, large ones are refined here so that
                     // their far parts stay on this lattice
-                    else if (p < g.pk && dmin < thr_p) act = (lev == 0 || rha <= hand_p * thr_p) ? ACT_HAND : ACT_REFINE;
+                    else if (p < pk && dmin < thr_p) act = (lev == 0 || rha <= hand_p * thr_p) ? ACT_HAND : ACT_REFINE;
                     // rim blocks: what lies within the shadowing ramp of their horizon goes down as well, in pieces of
                     // at most 0.05 rad
-                    else if (p < g.pk && limb && spread < 1.5607f &&
+                    else if (p < pk && limb && spread < 1.5607f &&
                              adc * __cosf(spread) - sqrtf(fmaxf(1.f - adc * adc, 0.f)) * ss < xthr)
                         act = (lev == 0 || rha <= 0.05f) ? ACT_HAND : ACT_REFINE;
                     else if (lev > 0 && (rha > rcap || rha * rha > kappa2 * (alpha2 + dmin * dmin) ||
@@ -890,7 +913,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
             }
             __syncwarp();
         }
-        if (p < g.pk && lane == 0) {
+        if (p < pk && lane == 0) {
             const int nbI = (NG + 3) / 4;
             if (out_cur >= 0) {
                 g.pool_out[(size_t)out_cur * CHUNK] = -1;
@@ -902,13 +925,13 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
             if (sp_max > g.status[1]) atomicMax(g.status + 1, sp_max);
             if (out_n > g.status[2 + p]) atomicMax(g.status + 2 + p, out_n);
         }
-    } else if (p < g.pk && lane == 0) {
+    } else if (p < pk && lane == 0) {
         const int nbJ = (NG + 7) / 8, nbI = (NG + 3) / 4;
         const int bI = I0 >> 2, bJ = J0 >> 3;
         if (bI < nbI && bJ < nbJ) g.heads_out[(size_t)k * nbI * nbJ + (size_t)bI * nbJ + bJ] = -1;
     }
     __syncthreads();  // stacks and buffers are dead: the reduction reuses the memory
-    tile_writeback(g, red, k, ti, tj, a0, a1, a2, false);
+    tile_writeback(g, p, red, k, ti, tj, a0, a1, a2, false);
 }
 
 // ---- diffuse lobe: one pass, writes `out`.  1x1 lattice whose node carries the covariance of the refmap cell (fourth
@@ -922,14 +945,17 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeAr
 
     const int k = blockIdx.y;
     const TreeConst rc = g.rc[k];
-    const int tiles_x = ((g.res << g.p) + 15) / 16;
+    const int p = g.diff_cov ? 0 : rc.pk;  // the grid is sized for the finest lattice of the call
+    const bool pixcov = g.diff_cov && rc.pk > 0;
+    const int tiles_x = ((g.res << p) + 15) / 16;
+    if ((int)blockIdx.x >= tiles_x * tiles_x) return;
     const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
     const int I0 = ti * 16 + (warp >> 1) * 4, J0 = tj * 16 + (warp & 1) * 8;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     NodeT nd;
-    make_node(g, rc, I0 + (lane >> 3), J0 + (lane & 7), false, nd);
+    make_node(g, rc, p, pixcov, I0 + (lane >> 3), J0 + (lane & 7), false, nd);
     float ax, ay, az, beta;
-    const bool live = rc.has_diff && warp_cone(g, nd, ax, ay, az, beta);
+    const bool live = rc.has_diff && warp_cone(g, p, nd, ax, ay, az, beta);
     if (live) {
         const float4* pyr = g.pyr_d + (size_t)rc.env * g.gd.cells * REC4;
         const float* env_b = g.env + (size_t)rc.env * g.He * g.We * 3;
@@ -945,7 +971,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeAr
                 const float4 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4], s5 = s[5], s6 = s[6];
                 float x = nd.nx * s0.x + nd.ny * s0.y + nd.nz * s0.z;
                 float nSn = nd.q0 * s1.x + nd.q1 * s1.y + nd.q2 * s1.z + nd.q3 * s2.x + nd.q4 * s2.y + nd.q5 * s2.z;
-                if (g.pixcov)
+                if (pixcov)
                     nSn += s0.x * s0.x * nd.P0 + s0.y * s0.y * nd.P1 + s0.z * s0.z * nd.P2 + s0.x * s0.y * nd.P3 +
                            s0.x * s0.z * nd.P4 + s0.y * s0.z * nd.P5;
                 const float w = fast_sqrt(3.f * fmaxf(nSn, 0.f));
@@ -1077,7 +1103,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeAr
         a0 *= wn * rc.cdiff[0]; a1 *= wn * rc.cdiff[1]; a2 *= wn * rc.cdiff[2];
     }
     __syncthreads();
-    tile_writeback(g, red, k, ti, tj, a0, a1, a2, true);
+    tile_writeback(g, p, red, k, ti, tj, a0, a1, a2, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1143,13 +1169,17 @@ static int log2_exact(int S) {
     return -1;
 }
 
+static constexpr int TREE_CHUNK = 64;  // renders per launch sequence: bounds the workspace for large batches
+
+// S: 1, 2, 4, 8, 16 = that footprint for every render; 0 = per render (given, or chosen on the device): sized for 16
 static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
     make_geom(L.gs, He, We, 1);
     // the diffuse lobe reads no cell wider than ~0.03 rad: level 3 at 1000 rows, level 1 at 250 rows
     int dbase = 0;
     while ((2 << dbase) * M_PI / He <= 0.03) ++dbase;
     make_geom(L.gd, He, We, dbase);
-    L.pk = log2_exact(S);
+    L.pk = S > 0 ? log2_exact(S) : TREE_MAX_P;
+    const int NC = N < TREE_CHUNK ? N : TREE_CHUNK;
     Carver c(ws);
     L.status = c.take<int>(64);
     L.rc = c.take<TreeConst>(N);
@@ -1158,7 +1188,7 @@ static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We,
     L.cos_t = c.take<float>(He);
     L.sin_p = c.take<float>(We);
     L.cos_p = c.take<float>(We);
-    L.pyr_s = c.take<float4>((size_t)N * L.gs.cells * REC4);
+    L.pyr_s = c.take<float4>((size_t)NC * L.gs.cells * REC4);
     L.pyr_d = c.take<float4>((size_t)B * L.gd.cells * REC4);
     // hand-over lists: pass p writes nblocks[p] chains that pass p + 1 reads; two pools alternate, sized for the average
     // list (the longest ones, at the limb, reach ~3000 entries) with a factor 3 of slack
@@ -1170,9 +1200,9 @@ static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We,
         // hands most of the map down), 1: 8, 2: 3.7, 3: 1.3; the longest single list was 26 chunks
         static const size_t budget[TREE_MAX_P] = {64, 24, 10, 6};
         const size_t per_block = budget[p];
-        const size_t n = (size_t)N * L.nblocks[p] * per_block + 64;
+        const size_t n = (size_t)NC * L.nblocks[p] * per_block + 64;
         if (n > need[p & 1]) need[p & 1] = n;
-        if ((size_t)N * L.nblocks[p] > needh[p & 1]) needh[p & 1] = (size_t)N * L.nblocks[p];
+        if ((size_t)NC * L.nblocks[p] > needh[p & 1]) needh[p & 1] = (size_t)NC * L.nblocks[p];
     }
     for (int i = 0; i < 2; ++i) {
         L.pool_cap[i] = (int)(need[i] < 0x7fffffff / CHUNK ? need[i] : 0x7fffffff / CHUNK);
@@ -1191,7 +1221,7 @@ static_assert(BUF1 * SREC4 <= (BUF1 / 2) * PAIR4 + 8 * BUF0, "the diffuse pass s
 using namespace drm;
 
 extern "C" size_t drm_render_workspace_bytes(int N, int B, int He, int We, int res, int S) {
-    if (N <= 0 || B <= 0 || He <= 0 || We <= 0 || res <= 0 || log2_exact(S) < 0) return 0;
+    if (N <= 0 || B <= 0 || He <= 0 || We <= 0 || res <= 0 || (S != 0 && log2_exact(S) < 0)) return 0;
     if ((long)He * We >= (1L << 28)) return 0;
     TreeLayout L;
     return tree_layout(L, nullptr, N, B, He, We, res, S);
@@ -1210,32 +1240,37 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
                                        void* cuda_stream, const DrmRenderOptions* opts) {
     DRM_REQUIRE(env && z6 && view3 && out, "render: null pointer");
     DRM_REQUIRE(N > 0 && B > 0 && He > 0 && We > 0 && res > 0, "render: N=%d B=%d He=%d We=%d res=%d must be positive", N, B, He, We, res);
-    DRM_REQUIRE(log2_exact(S) >= 0, "render: footprint_S=%d must be 1, 2, 4, 8 or 16", S);
+    DRM_REQUIRE(S == 0 || log2_exact(S) >= 0, "render: footprint_S=%d must be 0 (per render) or 1, 2, 4, 8, 16", S);
     DRM_REQUIRE(res <= 4096, "render: res=%d too large", res);
-    DRM_REQUIRE(N <= 65535 && B <= 65535, "render: at most 65535 renders / envmaps per call (N=%d, B=%d)", N, B);
+    DRM_REQUIRE(B <= 65535, "render: at most 65535 envmaps per call (B=%d)", B);
     DRM_REQUIRE((long)He * We < (1L << 28), "render: envmap of %d x %d texels is too large", He, We);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DrmRenderOptions o;
+    drm_render_default_options(&o);
+    if (opts) o = *opts;
+    const int32_t* S_per_render = o.footprint_per_render;
+    const int S_layout = S_per_render ? 0 : S;
     TreeLayout L;
-    const size_t need = tree_layout(L, workspace, N, B, He, We, res, S);
+    const size_t need = tree_layout(L, workspace, N, B, He, We, res, S_layout);
     if (!workspace || workspace_bytes < need) {
         set_error("render: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
         return DRM_EWORKSPACE;
     }
-    DrmRenderOptions o;
-    drm_render_default_options(&o);
-    if (opts) o = *opts;
     if (!(alpha_min > 0.f)) alpha_min = fmaxf(1e-3f, (float)(1.25 * M_PI / He));
 
     TreeArgs g;
     memset(&g, 0, sizeof(g));
-    g.env = env; g.rc = L.rc; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
-    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.out = out; g.status = L.status; g.env_used = L.env_used;
+    g.env = env; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
+    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.status = L.status; g.env_used = L.env_used;
     g.gs = L.gs; g.gd = L.gd;
-    g.B = B; g.He = He; g.We = We; g.N = N; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
+    g.B = B; g.He = He; g.We = We; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
     g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub;
-    gauss_legendre_t(S, g.fx, g.fw);
+    for (int p = 0; p <= TREE_MAX_P; ++p) gauss_legendre_t(1 << p, g.glx[p], g.glw[p]);
+    // the diffuse lobe: 1x1 lattice whose node carries the cell's covariance, or the render's own lattice when the cells
+    // are too wide for that (coarse refmaps) or the covariance is switched off
+    g.diff_cov = (o.pixel_covariance && g.cell <= 0.06f) ? 1 : 0;
 
     const int tb = 128;
     DRM_CHECK_CUDA(cudaMemsetAsync(L.status, 0, 64 * sizeof(int), st));
@@ -1245,21 +1280,12 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     const float grow = (float)fmin(10.0, pow(fmax(1.0, (M_PI / res) / (M_PI / 128.0)), 1.5));
     tree_setup_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(z6, view3, flip, env_index, N, B, alpha_min, g.cell,
                                                        o.level_scale * grow, (o.pixel_covariance ? o.level_scale0 : o.level_scale) * grow,
-                                                       o.full_second_order ? o.alpha_full2 : 1e30f, o.pixel_covariance, o.flat_scale, L.rc, L.status);
+                                                       o.full_second_order ? o.alpha_full2 : 1e30f, o.pixel_covariance, o.flat_scale,
+                                                       S, S_per_render, L.rc, L.status);
     DRM_CHECK_CUDA(cudaMemsetAsync(L.env_used, 0, sizeof(int) * B, st));
     tree_mark_used_kernel<<<(N + tb - 1) / tb, tb, 0, st>>>(L.rc, N, L.env_used);
     count_launches(3);
-    // ---- pyramids --------------------------------------------------------------------------------------------------
-    if (L.gs.L >= 1) {
-        const int n1 = L.gs.H[1] * L.gs.W[1];
-        pyr_from_texels_kernel<true><<<dim3((n1 + tb - 1) / tb, N), tb, 0, st>>>(g, 1, L.pyr_s);
-        count_launches(1);
-        for (int l = 2; l <= L.gs.L; ++l) {
-            const int nl = L.gs.H[l] * L.gs.W[l];
-            pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, N), tb, 0, st>>>(L.gs, l, L.pyr_s, nullptr);
-            count_launches(1);
-        }
-    }
+    // ---- diffuse pyramids of the envmaps in use (view independent: shared by every render of an envmap) --------------
     if (L.gd.L >= 1) {
         const int first = L.gd.base > 0 ? L.gd.base : 1;  // base 0: texels are read directly, level 1 is the first stored
         const int nb = L.gd.H[first] * L.gd.W[first];
@@ -1271,35 +1297,48 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
             count_launches(1);
         }
     }
-    // ---- diffuse lobe (writes out), then the specular passes (add) ---------------------------------------------------
     DRM_CHECK_CUDA(cudaFuncSetAttribute(tree_diff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM));
     DRM_CHECK_CUDA(cudaFuncSetAttribute(tree_spec_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_SMEM));
-    {
+    // ---- renders, TREE_CHUNK at a time: specular pyramids, diffuse lobe (writes out), specular passes (add) ------------
+    const size_t per_render_out = (size_t)res * res * 3;
+    for (int k0 = 0; k0 < N; k0 += TREE_CHUNK) {
+        const int n = N - k0 < TREE_CHUNK ? N - k0 : TREE_CHUNK;
         TreeArgs a = g;
-        const bool cov = o.pixel_covariance && L.pk > 0 && g.cell <= 0.06f;
-        a.p = (L.pk > 0 && !cov) ? L.pk : 0;
-        a.pixcov = cov ? 1 : 0;
-        gauss_legendre_t(1 << a.p, a.glx, a.glw);
-        const int NGd = res << a.p;
-        const int tiles = ((NGd + 15) / 16) * ((NGd + 15) / 16);
-        tree_diff_kernel<<<dim3(tiles, N), TREE_THREADS, TREE_SMEM, st>>>(a);
-        count_launches(1);
-    }
-    for (int p = 0; p <= L.pk; ++p) {
-        TreeArgs a = g;
-        a.p = p;
-        a.pixcov = (o.pixel_covariance && p == 0 && L.pk > 0) ? 1 : 0;
-        gauss_legendre_t(1 << p, a.glx, a.glw);
-        if (p > 0) { a.pool_in = L.pool[(p - 1) & 1]; a.heads_in = L.heads[(p - 1) & 1]; }
-        if (p < L.pk) {
-            a.pool_out = L.pool[p & 1]; a.heads_out = L.heads[p & 1]; a.pool_cap = L.pool_cap[p & 1];
-            a.pool_ctr = L.status + 8 + p;
-            DRM_CHECK_CUDA(cudaMemsetAsync(a.pool_ctr, 0, sizeof(int), st));
+        a.rc = L.rc + k0;
+        a.N = n;
+        a.out = out + (size_t)k0 * per_render_out;
+        if (L.gs.L >= 1) {
+            const int n1 = L.gs.H[1] * L.gs.W[1];
+            pyr_from_texels_kernel<true><<<dim3((n1 + tb - 1) / tb, n), tb, 0, st>>>(a, 1, L.pyr_s);
+            count_launches(1);
+            for (int l = 2; l <= L.gs.L; ++l) {
+                const int nl = L.gs.H[l] * L.gs.W[l];
+                pyr_merge_kernel<<<dim3((nl + tb - 1) / tb, n), tb, 0, st>>>(L.gs, l, L.pyr_s, nullptr);
+                count_launches(1);
+            }
         }
-        const int NG = res << p;
-        const int tiles = ((NG + 15) / 16) * ((NG + 15) / 16);
-        tree_spec_pass_kernel<<<dim3(tiles, N), TREE_THREADS, TREE_SMEM, st>>>(a);
-        count_launches(1);
+        {
+            const int pd = a.diff_cov ? 0 : L.pk;  // grid for the finest lattice a render of this call may have
+            const int NGd = res << pd;
+            const int tiles = ((NGd + 15) / 16) * ((NGd + 15) / 16);
+            tree_diff_kernel<<<dim3(tiles, n), TREE_THREADS, TREE_SMEM, st>>>(a);
+            count_launches(1);
+        }
+        for (int p = 0; p <= L.pk; ++p) {
+            a.p = p;
+            a.pixcov = (o.pixel_covariance && p == 0) ? 1 : 0;
+            a.pool_in = nullptr; a.heads_in = nullptr; a.pool_out = nullptr; a.heads_out = nullptr; a.pool_ctr = nullptr;
+            if (p > 0) { a.pool_in = L.pool[(p - 1) & 1]; a.heads_in = L.heads[(p - 1) & 1]; }
+            if (p < L.pk) {
+                a.pool_out = L.pool[p & 1]; a.heads_out = L.heads[p & 1]; a.pool_cap = L.pool_cap[p & 1];
+                a.pool_ctr = L.status + 8 + p;
+                DRM_CHECK_CUDA(cudaMemsetAsync(a.pool_ctr, 0, sizeof(int), st));
+            }
+            const int NG = res << p;
+            const int tiles = ((NG + 15) / 16) * ((NG + 15) / 16);
+            tree_spec_pass_kernel<<<dim3(tiles, n), TREE_THREADS, TREE_SMEM, st>>>(a);
+            count_launches(1);
+        }
     }
     DRM_CHECK_CUDA(cudaGetLastError());
     return DRM_OK;
@@ -1331,6 +1370,7 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->limb_boost = 2.f;
     o->limb_x = 8.f;
     o->flat_scale = 1.4f;
+    o->footprint_per_render = nullptr;
     o->limb_sub = 0.f;
     o->limb_hand = 1e30f;
     o->limb_ramp = 0.f;

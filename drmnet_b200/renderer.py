@@ -15,6 +15,7 @@ models/drmnet.py:561-569 and :680-691.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import List, Optional, Sequence
 
@@ -110,56 +111,72 @@ def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor
     if flip is not None:
         flip = flip.to(device=device, dtype=torch.uint8).contiguous()
 
-    # footprint: one S for the whole batch, or one per render (None = from each render's roughness); renders are
-    # grouped by S and each group is one launch
+    # footprint: one S for the whole batch, one per render, or None = chosen per render from its roughness.  The
+    # hierarchical path takes all three in ONE launch sequence (the choice is made on the device: no host read of z);
+    # the single-level validation path runs one launch per distinct S.
+    per_render = None
     if footprint_S is None:
-        rough = z6[:, 4].clip(0, 1).tolist()  # one small device-to-host read
-        amin = alpha_min if alpha_min and alpha_min > 0 else default_alpha_min(He)
-        per_render = [auto_footprint(r, res, amin) for r in rough]
+        S_call = 0
     elif isinstance(footprint_S, int):
-        per_render = None
+        S_call = int(footprint_S)
     else:
-        per_render = [int(s) for s in (footprint_S.tolist() if isinstance(footprint_S, torch.Tensor) else footprint_S)]
-        if len(per_render) != N:
+        per_render = footprint_S if isinstance(footprint_S, torch.Tensor) else torch.tensor([int(s) for s in footprint_S])
+        if per_render.numel() != N:
             raise ValueError("footprint_S must be an int or have one entry per render")
-    if per_render is not None and len(set(per_render)) == 1:
-        footprint_S, per_render = per_render[0], None
+        per_render = per_render.to(device=device, dtype=torch.int32).contiguous()
+        S_call = 0
+    stream = torch.cuda.current_stream(device).cuda_stream
+    L = _lib.lib()
 
-    def launch(S, zz, vv, ee, ff, oo):
-        import ctypes
-        n = zz.shape[0]
-        L = _lib.lib()
-        nbytes = (L.drm_render_flat_workspace_bytes if flat else L.drm_render_workspace_bytes)(n, B, He, We, int(res), int(S))
-        if nbytes == 0:
-            raise ValueError(f"render_batch: unsupported sizes N={n} B={B} He={He} We={We} res={res} S={S}")
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        args = (envmaps.data_ptr(), B, He, We, ee.data_ptr(), zz.data_ptr(), vv.data_ptr(),
-                ff.data_ptr() if ff is not None else None, n, int(res), int(S), float(alpha_min), int(channel_first),
-                oo.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+    def common_args(S, zz, vv, ee, ff, oo, ws):
+        return (envmaps.data_ptr(), B, He, We, ee.data_ptr(), zz.data_ptr(), vv.data_ptr(),
+                ff.data_ptr() if ff is not None else None, zz.shape[0], int(res), int(S), float(alpha_min),
+                int(channel_first), oo.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+
+    with torch.cuda.device(device):
         if flat:
-            _lib.check(L.drm_render_refmaps_flat(*args))
-            return
-        _lib.check(L.drm_render_refmaps_opts(*args, ctypes.byref(options) if options is not None else None))
+            if footprint_S is None:
+                amin = alpha_min if alpha_min and alpha_min > 0 else default_alpha_min(He)
+                S_list = [auto_footprint(r, res, amin) for r in z6[:, 4].clip(0, 1).tolist()]
+            elif per_render is not None:
+                S_list = per_render.tolist()
+            else:
+                S_list = [S_call] * N
+            for S in sorted(set(S_list)):
+                ids = torch.tensor([i for i, s in enumerate(S_list) if s == S], device=device)
+                nbytes = L.drm_render_flat_workspace_bytes(ids.numel(), B, He, We, int(res), int(S))
+                if nbytes == 0:
+                    raise ValueError(f"render_batch: unsupported sizes N={ids.numel()} B={B} He={He} We={We} res={res} S={S}")
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+                part = out if len(set(S_list)) == 1 else torch.empty((ids.numel(),) + shape[1:], dtype=torch.float32, device=device)
+                _lib.check(L.drm_render_refmaps_flat(*common_args(
+                    S, z6[ids].contiguous(), view_from[ids].contiguous(), env_index[ids].contiguous(),
+                    flip[ids].contiguous() if flip is not None else None, part, ws)))
+                if part is not out:
+                    out.index_copy_(0, ids, part)
+            return out
+        nbytes = L.drm_render_workspace_bytes(N, B, He, We, int(res), 0 if per_render is not None else S_call)
+        if nbytes == 0:
+            raise ValueError(f"render_batch: unsupported sizes N={N} B={B} He={He} We={We} res={res} S={footprint_S} "
+                             "(footprints are 1, 2, 4, 8 or 16)")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        o = options
+        if per_render is not None:
+            o = _lib.RenderOptions()
+            ctypes.memmove(ctypes.byref(o), ctypes.byref(options if options is not None else _lib.default_render_options()),
+                           ctypes.sizeof(o))
+            o.footprint_per_render = per_render.data_ptr()
+        _lib.check(L.drm_render_refmaps_opts(*common_args(S_call, z6, view_from, env_index, flip, out, ws),
+                                             ctypes.byref(o) if o is not None else None))
         if check_status:
             st = (ctypes.c_int * 16)()
             _lib.check(L.drm_render_status(ws.data_ptr(), st, stream))
             torch.cuda.current_stream(device).synchronize()
             render_batch.last_status = list(st)
             if st[0]:
-                raise RuntimeError(f"render_batch: status {st[0]} (1: hand-over list overflow, 2: env_index out of range, "
-                                   f"4: traversal stack overflow); high-water marks {list(st)[1:]}")
-
-    with torch.cuda.device(device):
-        if per_render is None:
-            launch(footprint_S, z6, view_from, env_index, flip, out)
-        else:
-            for S in sorted(set(per_render)):
-                ids = torch.tensor([i for i, s in enumerate(per_render) if s == S], device=device)
-                part = torch.empty((ids.numel(),) + shape[1:], dtype=torch.float32, device=device)
-                launch(S, z6[ids].contiguous(), view_from[ids].contiguous(), env_index[ids].contiguous(),
-                       flip[ids].contiguous() if flip is not None else None, part)
-                out.index_copy_(0, ids, part)
+                raise RuntimeError(f"render_batch: status {st[0]} (1: hand-over pool exhausted, 2: env_index out of range, "
+                                   f"4: traversal stack overflow, 8: a footprint was not 1, 2, 4, 8 or 16); "
+                                   f"high-water marks {list(st)[1:]}")
     return out
 
 
@@ -259,9 +276,7 @@ class B200RefMapRenderer:
             # parameters that are not named keep their last value in the persistent scene
             self._bsdf = z6 = self._compose_z6(z, names, self._bsdf.to(self.device))
         res = self._film_res(sensor)
-        S = self.footprint_S
-        if S is None:
-            S = auto_footprint(float(z6[4].clip(0, 1)), res, self.alpha_min or default_alpha_min(env.shape[0]))
+        S = self.footprint_S  # None: chosen on the device from the roughness (no host read of z)
         img = render_batch(env[None], z6[None], view[None].to(self.device),
                            flip=torch.tensor([do_flip], device=self.device), res=res, footprint_S=S,
                            alpha_min=self.alpha_min or 0.0, channel_first=channel_first)[0]

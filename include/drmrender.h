@@ -49,7 +49,10 @@ int64_t drm_launch_count(void);
  *              (utils/mitsuba3_utils.py:237-242); unnamed parameters carry the scene defaults 0,0,0,0,0,1 (:348-361)
  *   view3      [N, 3] fp32 camera position (any positive length; the sensor looks at the origin, up = +Y, :235-236)
  *   flip       [N] uint8 (may be NULL = no flip): mirrors the refmap columns (:38-40)
- *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117); 1, 2, 4, 8 or 16
+ *   footprint_S  S x S Gauss-Legendre sub-normals per refmap cell (box pixel filter, :116-117): 1, 2, 4, 8 or 16 for
+ *              every render, or 0: per render -- DrmRenderOptions::footprint_per_render, else chosen on the device from
+ *              the render's roughness (cell width / lobe half-width: the rule of renderer.auto_footprint).  Renders
+ *              with different footprints run in the same launches
  *   alpha_min  lower clamp of the GGX alpha = roughness^2; <= 0 selects max(1e-3, 1.25*pi/He)
  *   channel_first  0: out [N, res, res, 3];  1: out [N, 3, res, res]   (:196-198)
  *   out        fp32 (device)
@@ -87,6 +90,8 @@ typedef struct DrmRenderOptions {
                                (default 0: off; with a finite limb_hand this is cheaper and accurate to ~3e-3 locally) */
     float flat_scale;       /* scale of the distances (in cells) beyond which a lattice is accurate because the lobe is
                                flat across the cell */
+    const int32_t* footprint_per_render;  /* device, [N]: footprint S of each render (1, 2, 4, 8, 16; <= 0: chosen from
+                               its roughness); NULL: footprint_S applies to every render */
 } DrmRenderOptions;
 
 void drm_render_default_options(DrmRenderOptions* opts);
