@@ -20,8 +20,8 @@ class RenderOptions(ctypes.Structure):
                 ("kappa_diffuse", ctypes.c_float), ("horizon_diffuse", ctypes.c_float),
                 ("level_scale", ctypes.c_float), ("level_scale0", ctypes.c_float),
                 ("pixel_covariance", ctypes.c_int), ("full_second_order", ctypes.c_int), ("alpha_full2", ctypes.c_float), ("hand_over", ctypes.c_float), ("limb_nv", ctypes.c_float),
-                ("limb_boost", ctypes.c_float), ("limb_x", ctypes.c_float), ("limb_sub", ctypes.c_float), ("limb_hand", ctypes.c_float),
-                ("limb_ramp", ctypes.c_float), ("flat_scale", ctypes.c_float), ("footprint_per_render", ctypes.c_void_p)]
+                ("limb_boost", ctypes.c_float), ("limb_x", ctypes.c_float), ("limb_cells", ctypes.c_float), ("limb_sub", ctypes.c_float), ("limb_hand", ctypes.c_float),
+                ("limb_ramp", ctypes.c_float), ("flat_scale", ctypes.c_float), ("footprint_per_render", ctypes.c_void_p), ("collect_stats", ctypes.c_int)]
 
 
 def default_render_options() -> "RenderOptions":
@@ -68,7 +68,7 @@ def lib() -> ctypes.CDLL:
     L.drm_render_default_options.restype = None
     L.drm_render_default_options.argtypes = [ctypes.POINTER(RenderOptions)]
     L.drm_render_status.restype = i32
-    L.drm_render_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 16), vp]
+    L.drm_render_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 40), vp]
     L.drm_render_flat_workspace_bytes.restype = sz
     L.drm_render_flat_workspace_bytes.argtypes = [i32] * 6
     L.drm_render_refmaps_flat.restype = i32

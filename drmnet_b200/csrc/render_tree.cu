@@ -79,8 +79,9 @@ struct TreeArgs {
     int pool_cap;          // chunks in pool_out
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
-    float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub;
+    float cell, domega_k, kappa, rcap, rcap_simple, hz, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub, limb_cells;
     float glx[TREE_MAX_P + 1][16], glw[TREE_MAX_P + 1][16];  // Gauss-Legendre lattices 1, 2, 4, 8, 16
+    int stats;                   // debug: count visits / accepted records per pass into status[16..]
     int diff_cov;                // diffuse pass: 1x1 lattice with the cell covariance (else the render's own lattice)
 };
 
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         }
         int out_n = 0, out_cur = -1, out_fill = 0, out_head = -1;
         int sp = 0, n1 = 0, n0 = 0, sp_max = 0;
+        int st_visits = 0, st_acc0 = 0, st_acc1 = 0, st_iters = 0;
         // at the limb (n.v -> 0) the lobe sits on the horizon of the normal and the cell average converges later
         const float nv_min = -warp_max(nd.active ? -nd.nv : -1.f);
         // ... and n.d = 2 (v.h)(n.h) - n.v moves by the cell's own spread of n.v, so where n.v comes within a few alpha of
@@ -584,7 +586,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         // coarse lattices: it all goes down to the render's own lattice.
         // (a lattice whose sub-cells are narrower than limb_sub * alpha resolves that ramp: no rim rule on it)
         const float subw = g.cell / (float)(1 << p);
-        const bool limb = nv_min < fmaxf(g.limb_nv, g.limb_x * sqrtf(rc.alpha2)) && subw * subw > g.limb_sub * g.limb_sub * rc.alpha2;
+        const bool limb = nv_min < fmaxf(g.limb_nv, fminf(g.limb_x * sqrtf(rc.alpha2), g.limb_cells * g.cell)) &&
+                          subw * subw > g.limb_sub * g.limb_sub * rc.alpha2;
         const float thr_p = rc.thr[p] * (limb ? g.limb_boost : 1.f);
         const float hand_p = limb ? g.limb_hand : g.hand;
         const float xthr = g.limb_ramp * sqrtf(rc.alpha2);
@@ -767,6 +770,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                 }
             }
             const bool has = lane < ntake;
+            st_visits += ntake; st_iters += 1;
             __syncwarp();
             // ---- decide ----
             int act = ACT_DROP;
@@ -910,6 +914,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                 }
                 n1 += __popc(m1);
                 n0 += __popc(m0);
+                st_acc1 += __popc(m1); st_acc0 += __popc(m0);
             }
             __syncwarp();
         }
@@ -920,6 +925,10 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                 g.pool_out[(size_t)out_cur * CHUNK + 1] = out_fill;
             }
             g.heads_out[(size_t)k * nbI * nbJ + (size_t)bI * nbJ + bJ] = out_head;
+        }
+        if (lane == 0 && g.stats) {
+            atomicAdd(g.status + 16 + 4 * p, st_visits); atomicAdd(g.status + 17 + 4 * p, st_iters);
+            atomicAdd(g.status + 18 + 4 * p, st_acc0); atomicAdd(g.status + 19 + 4 * p, st_acc1);
         }
         if (lane == 0) {  // high-water marks (drm_render_status)
             if (sp_max > g.status[1]) atomicMax(g.status + 1, sp_max);
@@ -1229,7 +1238,7 @@ extern "C" size_t drm_render_workspace_bytes(int N, int B, int He, int We, int r
 
 extern "C" int drm_render_status(const void* workspace, int* status_host, void* cuda_stream) {
     DRM_REQUIRE(workspace && status_host, "render_status: null pointer");
-    DRM_CHECK_CUDA(cudaMemcpyAsync(status_host, workspace, 16 * sizeof(int), cudaMemcpyDeviceToHost,
+    DRM_CHECK_CUDA(cudaMemcpyAsync(status_host, workspace, 40 * sizeof(int), cudaMemcpyDeviceToHost,
                                    static_cast<cudaStream_t>(cuda_stream)));
     return DRM_OK;
 }
@@ -1266,11 +1275,12 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     g.B = B; g.He = He; g.We = We; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
-    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub;
+    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub; g.limb_cells = o.limb_cells;
     for (int p = 0; p <= TREE_MAX_P; ++p) gauss_legendre_t(1 << p, g.glx[p], g.glw[p]);
     // the diffuse lobe: 1x1 lattice whose node carries the cell's covariance, or the render's own lattice when the cells
     // are too wide for that (coarse refmaps) or the covariance is switched off
     g.diff_cov = (o.pixel_covariance && g.cell <= 0.06f) ? 1 : 0;
+    g.stats = o.collect_stats;
 
     const int tb = 128;
     DRM_CHECK_CUDA(cudaMemsetAsync(L.status, 0, 64 * sizeof(int), st));
@@ -1371,7 +1381,9 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->limb_x = 8.f;
     o->flat_scale = 1.4f;
     o->footprint_per_render = nullptr;
+    o->collect_stats = 0;
     o->limb_sub = 0.f;
+    o->limb_cells = 1.3f;
     o->limb_hand = 1e30f;
     o->limb_ramp = 0.f;
 }

@@ -169,7 +169,7 @@ def render_batch(envmaps: torch.Tensor, z: torch.Tensor, view_from: torch.Tensor
         _lib.check(L.drm_render_refmaps_opts(*common_args(S_call, z6, view_from, env_index, flip, out, ws),
                                              ctypes.byref(o) if o is not None else None))
         if check_status:
-            st = (ctypes.c_int * 16)()
+            st = (ctypes.c_int * 40)()
             _lib.check(L.drm_render_status(ws.data_ptr(), st, stream))
             torch.cuda.current_stream(device).synchronize()
             render_batch.last_status = list(st)

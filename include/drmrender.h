@@ -81,9 +81,10 @@ typedef struct DrmRenderOptions {
     float alpha_full2;      /* ... for renders with alpha >= this */
     float hand_over;        /* a cell too near for a pass's lattice goes to the next pass once its radius is below
                                hand_over * (that lattice's distance); larger cells are refined first */
-    float limb_nv;          /* blocks of normals with min n.v below max(limb_nv, limb_x * alpha) ... */
+    float limb_nv;          /* blocks of normals with min n.v below max(limb_nv, min(limb_x * alpha, limb_cells cells)) ... */
     float limb_boost;       /* ... use lattice distances scaled by this (the cell average converges later at the limb) ... */
     float limb_x;           /* ... (the rim of the refmap) ... */
+    float limb_cells;       /* ... see limb_nv ... */
     float limb_sub;         /* ... on the lattices whose sub-cells are wider than limb_sub * alpha ... */
     float limb_hand;        /* hand_over of the rim blocks (default: unbounded, every near cell goes down whole) */
     float limb_ramp;        /* rim blocks also hand down what lies within limb_ramp * alpha of their horizon n.d = 0
@@ -92,6 +93,7 @@ typedef struct DrmRenderOptions {
                                flat across the cell */
     const int32_t* footprint_per_render;  /* device, [N]: footprint S of each render (1, 2, 4, 8, 16; <= 0: chosen from
                                its roughness); NULL: footprint_S applies to every render */
+    int collect_stats;      /* debug: count, per lattice pass, the pyramid cells visited and accepted (status words 16..35) */
 } DrmRenderOptions;
 
 void drm_render_default_options(DrmRenderOptions* opts);
@@ -103,10 +105,12 @@ int drm_render_refmaps_opts(const float* env, int B, int He, int We,
                             float* out, void* workspace, size_t workspace_bytes, void* cuda_stream,
                             const DrmRenderOptions* opts);
 
-/* Copies the 16 status words of a finished (or enqueued: the copy is stream-ordered) render to status_host[16]:
+/* Copies the 40 status words of a finished (or enqueued: the copy is stream-ordered) render to status_host[40]:
  * [0] flags, 0 = clean: bit 0 = the pool of hand-over lists ran out (result incomplete), bit 1 = an env_index was out of
  * range, bit 2 = a traversal stack overflowed (result incomplete); [1] deepest traversal stack; [2..6] longest hand-over
- * list written by passes 0..4; [8..11] chunks of 128 ints the passes 0..3 took from their pools. */
+ * list written by passes 0..4; [8..11] chunks of 128 ints the passes 0..3 took from their pools; with
+ * DrmRenderOptions::collect_stats, [16 + 4p ..]: cells visited, traversal iterations, texels accepted, pyramid cells
+ * accepted by pass p (summed over its blocks of 32 lattice nodes; they wrap for large batches). */
 int drm_render_status(const void* workspace, int* status_host, void* cuda_stream);
 
 /* Single-level evaluation of the same sum: every (sub-normal, texel) pair, S x S lattice, texels streamed by TMA
