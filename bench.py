@@ -420,13 +420,15 @@ def main():
             end = ev[-1]
         barrier()
     ms_own = ev[0].elapsed_time(end)
+    ms_compute = ev[0].elapsed_time(ev[-1])  # this rank's own kernels, before it waits for the other ranks' blocks
     launches = L.drm_launch_count() - launches0
-    t = torch.tensor([ms_own], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_own, ms_compute], dtype=torch.float64, device=dev)
     all_ms = [t.clone() for _ in range(world)]
     if world > 1:
         dist.all_gather(all_ms, t)
-    rank_ms = [float(x.item()) / args.steps for x in all_ms]
-    ms = max(float(x.item()) for x in all_ms)
+    rank_ms = [float(x[0].item()) / args.steps for x in all_ms]
+    rank_compute_ms = [float(x[1].item()) / args.steps for x in all_ms]
+    ms = max(float(x[0].item()) for x in all_ms)
     ms_per_step = ms / args.steps
     value = units * world * args.steps / (ms / 1e3)
 
@@ -455,7 +457,10 @@ def main():
             "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
             "config": dict(W["config"], parallelism=f"dp{world}",
                            collective="one equal-count all_gather of the results on a side stream" if gather else "none"),
-            "rank_ms": {"per_rank": rank_ms, "min": min(rank_ms), "max": max(rank_ms)},
+            "rank_ms": {"per_rank": rank_ms, "min": min(rank_ms), "max": max(rank_ms),
+                        "compute_only_per_rank": rank_compute_ms,
+                        "note": "per_rank includes waiting for the gathered blocks of the slowest rank; compute_only is the "
+                                "rank's own kernels (different BRDF draws per rank: the footprint mix sets it)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ncu_summary(args.workload) or {}).get("dram_bytes_per_step"),
                          "algorithmic_bytes_per_step": W["alg_bytes"], "peak_source": peak_src,

@@ -43,6 +43,7 @@ static constexpr int BUF1 = 32;        // staged pyramid records per warp
 static constexpr int BUF0 = 32;        // staged texel records per warp
 static constexpr int TREE_MAX_P = 4;   // lattices 1,2,4,8,16
 static constexpr int CHUNK = 128;      // ints per chunk of a hand-over list (2 header + 126 entries)
+static constexpr int TREE_CHUNK = 64;  // renders per launch sequence: bounds the workspace for large batches
 
 struct PyrGeom {
     int L, base;                 // top level; first stored level (1 for the specular pyramid; the diffuse one starts where
@@ -70,12 +71,15 @@ struct TreeArgs {
     float* out;
     int* status;           // [0]: list / stack overflow flag
     const int* env_used;   // [B] envmaps whose diffuse pyramid this call reads
+    const int* act;        // [TREE_MAX_P + 1][TREE_CHUNK] renders active in pass p, and their number
+    const int* nact;
     // hand-over lists: chains of CHUNK-int chunks ([0] next chunk or -1, [1] entries, [2..] entries) in a pool per pass
     const int* pool_in;    // chunks written by the previous pass
     const int* heads_in;   // [N][blocks of the previous pass] first chunk or -1
     int* pool_out;         // this pass's pool, heads and allocation counter
     int* heads_out;
     int* pool_ctr;
+    int* item_ctr;         // work counter of this pass's persistent CTAs
     int pool_cap;          // chunks in pool_out
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
@@ -285,6 +289,17 @@ __device__ __forceinline__ void texel_diff(const TreeArgs& g, const float* __res
 __global__ void tree_mark_used_kernel(const TreeConst* __restrict__ rc, int N, int* __restrict__ used) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < N && rc[k].has_diff) used[rc[k].env] = 1;
+}
+
+// per lattice pass p: the renders of this chunk whose own lattice is at least 2^p (one thread: a chunk has <= 64 renders)
+__global__ void tree_active_kernel(const TreeConst* __restrict__ rc, int n, int* __restrict__ act, int* __restrict__ nact) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int p = 0; p <= TREE_MAX_P; ++p) {
+        int c = 0;
+        for (int k = 0; k < n; ++k)
+            if (rc[k].pk >= p) act[p * TREE_CHUNK + c++] = k;
+        nact[p] = c;
+    }
 }
 
 template <bool SPEC>
@@ -542,13 +557,23 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
     float4* buf0 = reinterpret_cast<float4*>(tree_smem + TREE_WARPS * STACK_CAP * 4 + TREE_WARPS * (BUF1 / 2) * PAIR4 * 16) + warp * (BUF0 * 2);
     float* red = reinterpret_cast<float*>(tree_smem);  // reused after the traversal: [256][3]
 
-    const int k = blockIdx.y;
-    const TreeConst rc = g.rc[k];
-    const int p = g.p, pk = rc.pk;
-    if (p > pk) return;  // this render's own lattice is coarser: its last pass has run (uniform over the CTA)
+    const int p = g.p;
     const int NG = g.res << p;
     const int tiles_x = (NG + 15) / 16;
-    const int ti = blockIdx.x / tiles_x, tj = blockIdx.x - ti * tiles_x;
+    const int n_items = g.nact[p] * tiles_x * tiles_x;
+    // persistent CTAs: items = (active render, tile of 16 x 16 lattice nodes), tile-major so that the renders interleave,
+    // handed out by a counter (the rim tiles take several times longer than the others)
+    __shared__ int next_item;
+    while (true) {
+    if (tid == 0) next_item = atomicAdd(g.item_ctr, 1);
+    __syncthreads();
+    const int item = next_item;
+    if (item >= n_items) break;
+    const int k = g.act[p * TREE_CHUNK + item % g.nact[p]];
+    const int tile = item / g.nact[p];
+    const TreeConst rc = g.rc[k];
+    const int pk = rc.pk;
+    const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
     const int I0 = ti * 16 + (warp >> 1) * 4, J0 = tj * 16 + (warp & 1) * 8;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     const bool pixcov = g.pixcov && p == 0 && pk > 0;  // the 1x1 node of a finer footprint carries the cell's covariance
@@ -941,6 +966,8 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
     }
     __syncthreads();  // stacks and buffers are dead: the reduction reuses the memory
     tile_writeback(g, p, red, k, ti, tj, a0, a1, a2, false);
+    __syncthreads();  // ... and the next item's traversal reuses it again
+    }
 }
 
 // ---- diffuse lobe: one pass, writes `out`.  1x1 lattice whose node carries the covariance of the refmap cell (fourth
@@ -1165,6 +1192,8 @@ struct TreeLayout {
     int pool_cap[2];
     int* status;
     int* env_used;
+    int* act;
+    int* nact;
     TreeConst* rc;
     float *sin_t, *cos_t, *sin_p, *cos_p;
     float4 *pyr_s, *pyr_d;
@@ -1177,8 +1206,6 @@ static int log2_exact(int S) {
         if ((1 << p) == S) return p;
     return -1;
 }
-
-static constexpr int TREE_CHUNK = 64;  // renders per launch sequence: bounds the workspace for large batches
 
 // S: 1, 2, 4, 8, 16 = that footprint for every render; 0 = per render (given, or chosen on the device): sized for 16
 static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We, int res, int S) {
@@ -1193,6 +1220,8 @@ static size_t tree_layout(TreeLayout& L, void* ws, int N, int B, int He, int We,
     L.status = c.take<int>(64);
     L.rc = c.take<TreeConst>(N);
     L.env_used = c.take<int>(B);
+    L.act = c.take<int>((TREE_MAX_P + 1) * TREE_CHUNK);
+    L.nact = c.take<int>(16);
     L.sin_t = c.take<float>(He);
     L.cos_t = c.take<float>(He);
     L.sin_p = c.take<float>(We);
@@ -1270,7 +1299,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     TreeArgs g;
     memset(&g, 0, sizeof(g));
     g.env = env; g.sin_t = L.sin_t; g.cos_t = L.cos_t; g.sin_p = L.sin_p; g.cos_p = L.cos_p;
-    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.status = L.status; g.env_used = L.env_used;
+    g.pyr_s = L.pyr_s; g.pyr_d = L.pyr_d; g.status = L.status; g.env_used = L.env_used; g.act = L.act; g.nact = L.nact;
     g.gs = L.gs; g.gd = L.gd;
     g.B = B; g.He = He; g.We = We; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
@@ -1317,6 +1346,8 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
         a.rc = L.rc + k0;
         a.N = n;
         a.out = out + (size_t)k0 * per_render_out;
+        tree_active_kernel<<<1, 32, 0, st>>>(a.rc, n, L.act, L.nact);
+        count_launches(1);
         if (L.gs.L >= 1) {
             const int n1 = L.gs.H[1] * L.gs.W[1];
             pyr_from_texels_kernel<true><<<dim3((n1 + tb - 1) / tb, n), tb, 0, st>>>(a, 1, L.pyr_s);
@@ -1345,8 +1376,11 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
                 DRM_CHECK_CUDA(cudaMemsetAsync(a.pool_ctr, 0, sizeof(int), st));
             }
             const int NG = res << p;
-            const int tiles = ((NG + 15) / 16) * ((NG + 15) / 16);
-            tree_spec_pass_kernel<<<dim3(tiles, n), TREE_THREADS, TREE_SMEM, st>>>(a);
+            const long items = (long)((NG + 15) / 16) * ((NG + 15) / 16) * n;  // upper bound: the active renders are fewer
+            const int grid = (int)(items < 148L * 2 ? items : 148L * 2);  // persistent CTAs: two resident per SM
+            a.item_ctr = L.status + 44 + p;
+            DRM_CHECK_CUDA(cudaMemsetAsync(a.item_ctr, 0, sizeof(int), st));
+            tree_spec_pass_kernel<<<grid, TREE_THREADS, TREE_SMEM, st>>>(a);
             count_launches(1);
         }
     }
