@@ -86,7 +86,8 @@ typedef struct DrmRenderOptions {
     float limb_x;           /* ... (the rim of the refmap) ... */
     float limb_cells;       /* ... see limb_nv ... */
     float limb_sub;         /* ... on the lattices whose sub-cells are wider than limb_sub * alpha ... */
-    float limb_hand;        /* hand_over of the rim blocks (default: unbounded, every near cell goes down whole) */
+    float limb_hand;        /* hand_over of the rim blocks (default unbounded: every near cell goes down whole; 8 is 12 %
+                               faster on the headline batch and leaves up to 1.5e-3 in single rim cells, 1 leaves 6e-3) */
     float limb_ramp;        /* rim blocks also hand down what lies within limb_ramp * alpha of their horizon n.d = 0
                                (default 0: off; with a finite limb_hand this is cheaper and accurate to ~3e-3 locally) */
     float flat_scale;       /* scale of the distances (in cells) beyond which a lattice is accurate because the lobe is

@@ -28,9 +28,8 @@ for i in [int(x) for x in sys.argv[2:]]:
         k = np.unravel_index(loc.argmax(), loc.shape)
         print(f"  {name:34s} rel-L2 {np.linalg.norm(a-b)/np.linalg.norm(b):.2e} local max {loc.max():.2e} at {k} p99.9 {np.quantile(loc,0.999):.2e}  {e0.elapsed_time(e1):.2f} ms")
     run("default")
-    run("limb_hand inf ramp 0 (old)", limb_hand=1e30, limb_ramp=0.0)
-    run("limb_hand 1", limb_hand=1.0)
+    run("limb_hand 8", limb_hand=8.0)
     run("limb_hand 4", limb_hand=4.0)
-    run("ramp 3", limb_ramp=3.0)
-    run("ramp 12", limb_ramp=12.0)
-    run("limb_hand .5 ramp 0 (= limb off)", limb_hand=0.5, limb_ramp=0.0)
+    run("limb_hand 2", limb_hand=2.0)
+    run("limb_hand 1", limb_hand=1.0)
+    run("limb_hand 4 boost 3", limb_hand=4.0, limb_boost=3.0)
