@@ -12,8 +12,8 @@ for x in rows[hdr + 1:]:
     cur.setdefault((int(x[0]), x[ki].split("(")[0].replace("void ", ""), x[gi]), {})[x[mi]] = float(x[vi].replace(",", ""))
 ids = sorted(cur)
 tabs = [k[0] for k in ids if "tree_tables" in k[1]]
-ngroups = 5
-# steps are groups of `ngroups` render calls; take the last complete device step before the e2e steps: the 2nd step
+ngroups = 1
+# one render call (one launch sequence) per step since the footprints share their launches; take the 2nd step (timed)
 start, end = tabs[ngroups], tabs[2 * ngroups] if len(tabs) > 2 * ngroups else 10 ** 9
 lines, tot, by = [], 0.0, {}
 group = -1
@@ -25,7 +25,7 @@ for k in ids:
     tot += t
     if "tree_tables" in k[1]:
         group += 1
-        lines.append(f"-- render call {group} (one footprint class) --")
+        lines.append(f"-- render call {group} --")
     by[k[1]] = by.get(k[1], 0) + t
     if t > 0.2:
         lines.append(f"{k[1]:42s} grid {k[2]:18s} {t:9.3f} ms  {m.get('smsp__inst_executed.sum', 0) / 1e9:8.2f} G warp-instr")
