@@ -18,7 +18,6 @@ namespace drm {
 
 static constexpr uint32_t KEY_NAN = 0xFFFFFFFFu;  // sentinel: colour sum is NaN (ignored by nanmedian, :30-31)
 static constexpr uint32_t CELL_NONE = 0x7FFFFFFFu, CELL_MULTI = 0x80000000u;
-static constexpr int SMALL_MAX = 48;  // cells up to this size are selected by one thread
 
 struct I2RArgs {
     const float* colors;
@@ -32,14 +31,21 @@ struct I2RArgs {
     int min_points, reduce_mode;
     int64_t pair_capacity;
     // workspace
-    int32_t* bin_count;   // [M]
-    int32_t* bin_offset;  // [M]
-    int32_t* cursor;      // [M]
+    int32_t* cnt_first;   // [M+1] pairs (cell, pixel) where the cell is the pixel's first one: their rank inside the
+                          //       cell's segment is the value the histogram atomic returned
+    int32_t* cnt_other;   // [M+1] the other pairs of pixels that fall into several cells (thr > step/2, or exact ties)
+    int32_t* cursor;      // [M]   placement counter of those other pairs (pass 1)
     int32_t* nan_count;   // [B]
     int32_t* nan_list;    // [total_n]  (image b owns the slice starting at offsets[b])
+    int32_t* bin_offset;  // [M+1] exclusive scan of cnt_first + cnt_other; [M] = number of pairs
     int32_t* block_sums;  // scan scratch
-    uint2* pairs;         // (key, global pixel index)
+    uint2* pairs;         // (cell tag << 26 | global pixel index, key): one 64-bit load gives (key << 32) | tag | pixel,
+                          // whose order inside a cell is the total order (key, pixel); tag = cell % SEL_CELLS
     uint32_t* cell0;      // [total_n] first cell of each pixel (CELL_NONE if none), bit 31 set if it has more cells
+    uint32_t* key0;       // [total_n] sum key of the pixel
+    int32_t* rank0;       // [total_n] rank of the pixel inside its first cell
+    int32_t* block_image; // [ceil(total_n / 256)] image of the first pixel of each 256-pixel block
+    int32_t* nankey_flag; // [B] set when some pixel of the image has a NaN colour sum
     int32_t* big_list;    // [M] cells left to the warp-per-cell select (large, NaN-angle members, mean mode)
     int32_t* big_count;   // [1]
     int32_t* status;      // bit 0: pair buffer overflow
@@ -78,139 +84,178 @@ __device__ __forceinline__ int image_of(const int64_t* __restrict__ offsets, int
     return lo;
 }
 
-// image of pixel p: one binary search per CTA (for its first pixel, by thread 0), then a short forward walk per thread
-__device__ __forceinline__ int image_of_cta(const int64_t* __restrict__ offsets, int B, int64_t p, int64_t cta_first) {
-    __shared__ int b0;
-    if (threadIdx.x == 0) b0 = image_of(offsets, B, cta_first);
-    __syncthreads();
-    int b = b0;
-    while (b + 1 < B && offsets[b + 1] <= p) ++b;
-    return b;
+// image of the first pixel of every 256-pixel block (one binary search per block, done once; the passes then walk
+// forward from it, usually zero steps)
+__global__ void i2r_block_image_kernel(const int64_t* __restrict__ offsets, int B, int64_t nblk, int32_t* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < nblk) out[k] = image_of(offsets, B, k * 256);
 }
 
 // monotone uint key of the fp32 channel sum; -0.0 and +0.0 share a key (torch compares them equal)
 __device__ __forceinline__ uint32_t sum_key(const float* __restrict__ c, int C) {
-    float s = c[0];
-    for (int k = 1; k < C; ++k) s = __fadd_rn(s, c[k]);  // ((c0 + c1) + c2), colors.sum(-1) at img2refmap.py:30
+    float s;  // ((c0 + c1) + c2), colors.sum(-1) at img2refmap.py:30
+    if (C == 3) {
+        s = __fadd_rn(__fadd_rn(c[0], c[1]), c[2]);
+    } else {
+        s = c[0];
+        for (int k = 1; k < C; ++k) s = __fadd_rn(s, c[k]);
+    }
     if (isnan(s)) return KEY_NAN;
     s = __fadd_rn(s, 0.0f);  // -0.0 -> +0.0
     uint32_t b = __float_as_uint(s);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// One warp-wide increment per distinct cell: lanes that target the same cell elect a leader (raster-ordered pixels
-// mostly share their neighbours' cell).  Returns the lane's rank inside its group and the group's base (PASS 1).
-__device__ __forceinline__ int warp_claim(int32_t* counter, bool valid, int64_t gbin, bool want_base, int& rank) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned long long key = valid ? (unsigned long long)gbin : (0x8000000000000000ull | lane);
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(grp) - 1;
-    rank = __popc(grp & ((1u << lane) - 1u));
-    int base = 0;
-    if (valid && (int)lane == leader) {
-        if (want_base) base = atomicAdd(&counter[gbin], __popc(grp));
-        else atomicAdd(&counter[gbin], __popc(grp));
-    }
-    if (want_base) base = __shfl_sync(0xffffffffu, base, leader);
-    return base;
+// The cells of one axis whose window holds the angle x: centres are (arange + 0.5) * (pi / res) (img2refmap.py:16) and
+// the fp32 predicate |centre - x| <= thr (:27) alone decides membership.  The rounded difference is monotone in the
+// cell index, so the members are one run [lo, hi]: the candidates (+-1 cell for rounding) are trimmed from both ends.
+__device__ __forceinline__ bool axis_cells(const I2RArgs& a, float x, int& lo, int& hi) {
+    // floor() and the int conversion in one saturating instruction: +-inf and huge angles give an empty range
+    lo = max(__float2int_rd((x - a.thr) * a.inv_step - 0.5f), 0);
+    hi = min(__float2int_rd((x + a.thr) * a.inv_step - 0.5f), a.res - 2) + 1;
+    const float thr = a.thr, step = a.stepf;
+    while (lo <= hi && fabsf(__fsub_rn(__fmul_rn((float)lo + 0.5f, step), x)) > thr) ++lo;
+    while (hi > lo && fabsf(__fsub_rn(__fmul_rn((float)hi + 0.5f, step), x)) > thr) --hi;
+    return lo <= hi;
 }
 
-// PASS 0: angles, window predicate, histogram of the cells, first cell of each pixel left in cell0
-__global__ void __launch_bounds__(256) i2r_hist_pass(I2RArgs a) {
-    const int64_t cta_first = blockIdx.x * (int64_t)blockDim.x;
-    const int64_t p = cta_first + threadIdx.x;
-    const bool in_range = p < a.total_n;
-    const int b = image_of_cta(a.offsets, a.B, in_range ? p : a.total_n - 1, cta_first);
-    if (!in_range) return;
-    const int64_t base = a.offsets[b];
-    float th, ph;
+__device__ __forceinline__ void load_angles(const I2RArgs& a, int64_t p, float& th, float& ph) {
     if (a.is_thetaphi) {
-        th = a.geom[2 * p];
-        ph = a.geom[2 * p + 1];
+        const float2 v = reinterpret_cast<const float2*>(a.geom)[p];
+        th = v.x;
+        ph = v.y;
     } else {
         normal_to_thetaphi(a.geom[3 * p], a.geom[3 * p + 1], a.geom[3 * p + 2], th, ph);
     }
-    if (isnan(th) || isnan(ph)) {
-        // 'NaN > thr' is False (img2refmap.py:27): the pixel is a member of every cell of its image
-        const int slot = atomicAdd(&a.nan_count[b], 1);
-        a.nan_list[base + slot] = (int32_t)(p - base);
-        a.cell0[p] = CELL_NONE;
-        return;
-    }
-    bool have = false, multi = false;
-    int64_t first = 0;
-    // candidate cells: those whose centre can lie within thr of the angle, +-1 for rounding; the fp32 predicate below
-    // alone decides membership
-    const float lim = (float)a.res + (float)a.R + 1.f;
-    const float flo_i = floorf((th - a.thr) * a.inv_step - 0.5f), fhi_i = floorf((th + a.thr) * a.inv_step - 0.5f);
-    const float flo_j = floorf((ph - a.thr) * a.inv_step - 0.5f), fhi_j = floorf((ph + a.thr) * a.inv_step - 0.5f);
-    if (fhi_i > -lim && flo_i < lim && fhi_j > -lim && flo_j < lim) {  // also rejects +-inf
-        const int ilo = max((int)fmaxf(flo_i, -lim), 0), ihi = min((int)fminf(fhi_i, lim) + 1, a.res - 1);
-        const int jlo = max((int)fmaxf(flo_j, -lim), 0), jhi = min((int)fminf(fhi_j, lim) + 1, a.res - 1);
-        for (int i = ilo; i <= ihi; ++i) {
-            const float ci = __fmul_rn((float)i + 0.5f, a.stepf);  // (arange + 0.5) * (pi / res), img2refmap.py:16
-            if (fabsf(__fsub_rn(ci, th)) > a.thr) continue;
-            for (int j = jlo; j <= jhi; ++j) {
-                const float cj = __fmul_rn((float)j + 0.5f, a.stepf);
-                if (fabsf(__fsub_rn(cj, ph)) > a.thr) continue;
-                const int64_t gbin = (int64_t)b * a.res2 + (int64_t)i * a.res + j;
-                if (!have) { have = true; first = gbin; }
-                else multi = true;
-                atomicAdd(&a.bin_count[gbin], 1);
-            }
-        }
-    }
-    a.cell0[p] = have ? ((uint32_t)first | (multi ? CELL_MULTI : 0u)) : CELL_NONE;
 }
 
-// PASS 1: scatter (sum key, pixel) pairs into the cell segments
-__global__ void __launch_bounds__(256) i2r_scatter_pass(I2RArgs a) {
-    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool in_range = p < a.total_n;
-    const uint32_t c0 = in_range ? a.cell0[p] : CELL_NONE;
-    const bool have = c0 != CELL_NONE;
-    const int64_t first = (int64_t)(c0 & ~CELL_MULTI);
-    uint32_t key = 0;
-    if (have) key = sum_key(a.colors + p * a.C, a.C);
-    int rank;
-    const int base = warp_claim(a.cursor, have, first, true, rank);
-    if (have) {
-        const int64_t slot = (int64_t)a.bin_offset[first] + base + rank;
-        if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(key, (uint32_t)p);
-        else atomicOr(a.status, 1);
+static constexpr int SEL_CELLS = 64;  // cells per CTA of the select kernel: a pair carries its cell id modulo this
+static constexpr int PIX_BITS = 26;   // ... above the pixel index, so one call takes up to 2^26 pixels
+static constexpr uint32_t PIX_MASK = (1u << PIX_BITS) - 1u;
+
+// PASS 0: angles, window, sum key, histogram of the cells.  Each pixel keeps (first cell, key, rank inside that cell) so
+// that pass 1 places it without touching its normal or colour again.  A thread takes HIST_PX pixels (256 apart): all
+// their loads are issued first, and the rank that the histogram atomic returns is only consumed by the stores at the
+// end, so the latency of one pixel's atomic hides behind the arithmetic of the next.
+static constexpr int HIST_PX = 2;
+__global__ void __launch_bounds__(256) i2r_hist_pass(I2RArgs a) {
+    int64_t p[HIST_PX];
+    bool in[HIST_PX];
+    float g[HIST_PX][3], col[HIST_PX][3];
+#pragma unroll
+    for (int u = 0; u < HIST_PX; ++u) {
+        p[u] = ((int64_t)blockIdx.x * HIST_PX + u) * 256 + threadIdx.x;
+        in[u] = p[u] < a.total_n;
+        const int64_t pc = in[u] ? p[u] : a.total_n - 1;
+        if (a.is_thetaphi) {
+            const float2 v = reinterpret_cast<const float2*>(a.geom)[pc];
+            g[u][0] = v.x; g[u][1] = v.y; g[u][2] = 0.f;
+        } else {
+            g[u][0] = a.geom[3 * pc]; g[u][1] = a.geom[3 * pc + 1]; g[u][2] = a.geom[3 * pc + 2];
+        }
+        if (a.C == 3) {
+            col[u][0] = a.colors[3 * pc]; col[u][1] = a.colors[3 * pc + 1]; col[u][2] = a.colors[3 * pc + 2];
+        }
     }
-    if (have && (c0 & CELL_MULTI)) {
-        // the pixel's other cells: recompute the window (same arithmetic as the histogram pass), skip the first one
+    uint32_t cell0[HIST_PX], key[HIST_PX];
+    int rank[HIST_PX];
+#pragma unroll
+    for (int u = 0; u < HIST_PX; ++u) {
+        cell0[u] = CELL_NONE;
+        rank[u] = 0;
+        if (!in[u]) continue;
+        float th, ph;
+        if (a.is_thetaphi) { th = g[u][0]; ph = g[u][1]; }
+        else normal_to_thetaphi(g[u][0], g[u][1], g[u][2], th, ph);
+        key[u] = a.C == 3 ? sum_key(col[u], 3) : sum_key(a.colors + p[u] * a.C, a.C);
+        int b = a.block_image[blockIdx.x * HIST_PX + u];
+        while (b + 1 < a.B && a.offsets[b + 1] <= p[u]) ++b;
+        if (key[u] == KEY_NAN) a.nankey_flag[b] = 1;
+        if (isnan(th) || isnan(ph)) {
+            // 'NaN > thr' is False (img2refmap.py:27): the pixel is a member of every cell of its image
+            const int64_t base = a.offsets[b];
+            const int slot = atomicAdd(&a.nan_count[b], 1);
+            a.nan_list[base + slot] = (int32_t)(p[u] - base);
+            continue;
+        }
+        int i0, i1, j0, j1;
+        if (!(axis_cells(a, th, i0, i1) && axis_cells(a, ph, j0, j1))) continue;
+        const int img0 = b * a.res2;
+        const int first = img0 + i0 * a.res + j0;
+        const bool multi = i1 > i0 || j1 > j0;
+        rank[u] = atomicAdd(&a.cnt_first[first], 1);
+        cell0[u] = (uint32_t)first | (multi ? CELL_MULTI : 0u);
+        if (multi)
+            for (int i = i0; i <= i1; ++i)
+                for (int j = (i == i0 ? j0 + 1 : j0); j <= j1; ++j) atomicAdd(&a.cnt_other[img0 + i * a.res + j], 1);
+    }
+#pragma unroll
+    for (int u = 0; u < HIST_PX; ++u) {
+        if (!in[u]) continue;
+        a.cell0[p[u]] = cell0[u];
+        a.key0[p[u]] = key[u];
+        a.rank0[p[u]] = rank[u];
+    }
+}
+
+__device__ __forceinline__ void place_pair(const I2RArgs& a, int64_t slot, int cell, uint32_t p, uint32_t key) {
+    if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(p | ((uint32_t)(cell % SEL_CELLS) << PIX_BITS), key);
+    else atomicOr(a.status, 1);
+}
+
+// PASS 1: place (pixel, key) in the cell segments.  Four pixels per thread: the three record streams are read with
+// 16-byte loads and the four segment-offset gathers are in flight together (the pass is latency-bound otherwise).
+static constexpr int SCATTER_PX = 4;
+__global__ void __launch_bounds__(256) i2r_scatter_pass(I2RArgs a) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // quad of pixels
+    const int64_t p0 = q * SCATTER_PX;
+    if (p0 >= a.total_n) return;
+    uint32_t c0[SCATTER_PX], key[SCATTER_PX];
+    int rank[SCATTER_PX], off[SCATTER_PX];
+    if (p0 + SCATTER_PX <= a.total_n) {
+        const uint4 c = reinterpret_cast<const uint4*>(a.cell0)[q], k = reinterpret_cast<const uint4*>(a.key0)[q];
+        const int4 r = reinterpret_cast<const int4*>(a.rank0)[q];
+        c0[0] = c.x; c0[1] = c.y; c0[2] = c.z; c0[3] = c.w;
+        key[0] = k.x; key[1] = k.y; key[2] = k.z; key[3] = k.w;
+        rank[0] = r.x; rank[1] = r.y; rank[2] = r.z; rank[3] = r.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < SCATTER_PX; ++u) {
+            const bool in = p0 + u < a.total_n;
+            c0[u] = in ? a.cell0[p0 + u] : CELL_NONE;
+            key[u] = in ? a.key0[p0 + u] : 0u;
+            rank[u] = in ? a.rank0[p0 + u] : 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < SCATTER_PX; ++u) off[u] = c0[u] != CELL_NONE ? a.bin_offset[c0[u] & ~CELL_MULTI] : 0;
+#pragma unroll
+    for (int u = 0; u < SCATTER_PX; ++u)
+        if (c0[u] != CELL_NONE) place_pair(a, (int64_t)off[u] + rank[u], (int)(c0[u] & ~CELL_MULTI), (uint32_t)(p0 + u), key[u]);
+    bool any_multi = false;
+#pragma unroll
+    for (int u = 0; u < SCATTER_PX; ++u) any_multi |= c0[u] != CELL_NONE && (c0[u] & CELL_MULTI);
+    if (!any_multi) return;
+#pragma unroll
+    for (int u = 0; u < SCATTER_PX; ++u) {
+        if (c0[u] == CELL_NONE || !(c0[u] & CELL_MULTI)) continue;
+        // the pixel's other cells: the same window arithmetic as pass 0; they fill the segment behind the first-cell pairs
+        const int64_t p = p0 + u;
         const int b = image_of(a.offsets, a.B, p);
         float th, ph;
-        if (a.is_thetaphi) {
-            th = a.geom[2 * p];
-            ph = a.geom[2 * p + 1];
-        } else {
-            normal_to_thetaphi(a.geom[3 * p], a.geom[3 * p + 1], a.geom[3 * p + 2], th, ph);
-        }
-        const float lim = (float)a.res + (float)a.R + 1.f;
-        const float flo_i = floorf((th - a.thr) * a.inv_step - 0.5f), fhi_i = floorf((th + a.thr) * a.inv_step - 0.5f);
-        const float flo_j = floorf((ph - a.thr) * a.inv_step - 0.5f), fhi_j = floorf((ph + a.thr) * a.inv_step - 0.5f);
-        const int ilo = max((int)fmaxf(flo_i, -lim), 0), ihi = min((int)fminf(fhi_i, lim) + 1, a.res - 1);
-        const int jlo = max((int)fmaxf(flo_j, -lim), 0), jhi = min((int)fminf(fhi_j, lim) + 1, a.res - 1);
-        for (int i = ilo; i <= ihi; ++i) {
-            const float ci = __fmul_rn((float)i + 0.5f, a.stepf);
-            if (fabsf(__fsub_rn(ci, th)) > a.thr) continue;
-            for (int j = jlo; j <= jhi; ++j) {
-                const float cj = __fmul_rn((float)j + 0.5f, a.stepf);
-                if (fabsf(__fsub_rn(cj, ph)) > a.thr) continue;
-                const int64_t gbin = (int64_t)b * a.res2 + (int64_t)i * a.res + j;
-                if (gbin == first) continue;
-                const int64_t slot = (int64_t)a.bin_offset[gbin] + atomicAdd(&a.cursor[gbin], 1);
-                if (slot < a.pair_capacity) a.pairs[slot] = make_uint2(key, (uint32_t)p);
-                else atomicOr(a.status, 1);
+        load_angles(a, p, th, ph);
+        int i0, i1, j0, j1;
+        if (!(axis_cells(a, th, i0, i1) && axis_cells(a, ph, j0, j1))) continue;
+        const int img0 = b * a.res2;
+        for (int i = i0; i <= i1; ++i)
+            for (int j = (i == i0 ? j0 + 1 : j0); j <= j1; ++j) {
+                const int g = img0 + i * a.res + j;
+                place_pair(a, (int64_t)a.bin_offset[g] + a.cnt_first[g] + atomicAdd(&a.cursor[g], 1), g, (uint32_t)p, key[u]);
             }
-        }
     }
 }
 
-// ---- exclusive scan of bin_count (3 small kernels; M <= B*res^2 ints) ----------------------------------------
+// ---- exclusive scan of cnt_first + cnt_other (3 small kernels; M + 1 <= B*res^2 + 1 ints) ----------------------------------------
 static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
@@ -238,13 +283,14 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
     return wprefix + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                           int32_t* __restrict__ block_sums, int64_t M) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int32_t* __restrict__ in, const int32_t* __restrict__ in2,
+                                                           int32_t* __restrict__ out, int32_t* __restrict__ block_sums,
+                                                           int64_t M) {
     const int64_t start = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (start + k < M) ? in[start + k] : 0;
+        v[k] = (start + k < M) ? in[start + k] + in2[start + k] : 0;
         s += v[k];
     }
     int total;
@@ -290,7 +336,7 @@ struct CellView {
     __device__ __forceinline__ uint64_t get(int e) const {  // (key << 32) | global pixel index
         if (e < nreg) {
             uint2 pr = seg[e];
-            return ((uint64_t)pr.x << 32) | pr.y;
+            return ((uint64_t)pr.y << 32) | (pr.x & PIX_MASK);
         }
         const int64_t idx = base + nan_list[e - nreg];
         return ((uint64_t)sum_key(colors + idx * C, C) << 32) | (uint32_t)idx;
@@ -305,71 +351,93 @@ __device__ __forceinline__ void write_cell(const I2RArgs& a, int64_t gbin, int64
     if (a.sel_index) a.sel_index[gbin] = filled ? (int32_t)(winner - base) : -1;
 }
 
-// k-th smallest of arr[0..n) (distinct 64-bit values), Hoare quickselect in place
-__device__ __forceinline__ uint64_t quickselect(uint64_t* arr, int n, int k) {
-    int l = 0, r = n - 1;
-    while (l < r) {
-        const uint64_t pivot = arr[(l + r) >> 1];
-        int i = l, j = r;
-        while (i <= j) {
-            while (arr[i] < pivot) ++i;
-            while (arr[j] > pivot) --j;
-            if (i <= j) {
-                const uint64_t t = arr[i]; arr[i] = arr[j]; arr[j] = t;
-                ++i; --j;
-            }
-        }
-        if (k <= j) r = j;
-        else if (k >= i) l = i;
-        else break;
-    }
-    return arr[k];
-}
+// Median mode, cells without NaN-angle members.  A CTA owns SEL_CELLS consecutive cells, i.e. one contiguous run of
+// pairs: the run (and each pair's cell tag, left by pass 1) is staged in shared memory with coalesced loads, then the
+// work is ELEMENT-parallel -- every staged pair counts the members of its own cell that are smaller (members are
+// distinct 64-bit values) and the one whose rank is the lower-median rank names the winner.  All lanes stay busy
+// whatever the cell sizes are; a warp's lanes belong to two or three neighbouring cells, so they read the same few
+// shared-memory words (broadcast).  The cells' outputs are then written by one thread per cell, coalesced.
+// Cells that do not fit (more than SEL_MAXN members, or a run beyond the staging buffer), cells with NaN-angle
+// members and the mean mode are queued for the warp-per-cell kernel.
+static constexpr int SEL_THREADS = 256, SEL_CAP = 3072, SEL_MAXN = 512;
 
-// One thread per cell: cells with up to SMALL_MAX members and no NaN-angle members, median mode; the others are queued
-// for the warp-per-cell kernel.  The consecutive cells of a CTA own one contiguous run of pairs: it is staged in
-// shared memory with coalesced loads and each thread quickselects its own segment there.
-static constexpr int SELECT_CAP = 6144;  // pairs staged per CTA (48 KB)
-static constexpr int SELECT_THREADS = 128;  // cells per CTA: 128 x SMALL_MAX members always fit the staging buffer
-__global__ void __launch_bounds__(SELECT_THREADS) i2r_select_small(I2RArgs a, int64_t M) {
-    __shared__ uint64_t buf[SELECT_CAP];
-    const int64_t g0 = blockIdx.x * (int64_t)blockDim.x;
-    const int64_t gbin = g0 + threadIdx.x;
-    const int64_t glast = min(g0 + (int64_t)blockDim.x, M) - 1;
-    const int64_t run0 = a.bin_offset[g0];
-    const int64_t run1 = (int64_t)a.bin_offset[glast] + a.bin_count[glast];
-    const int run = (int)(run1 - run0);
-    const bool staged = run <= SELECT_CAP;
-    if (staged)
-        for (int e = threadIdx.x; e < run; e += blockDim.x) {
-            const uint2 pr = a.pairs[run0 + e];
-            buf[e] = ((uint64_t)pr.x << 32) | pr.y;
-        }
+// rank + (v < mine) for 64-bit values: v < mine exactly when mine + ~v (= mine - v - 1 mod 2^64) carries out, so the
+// comparison is one add-with-carry chain and its carry is added to the rank -- no predicates, no selects
+// (the staging buffer holds ~v)
+__device__ __forceinline__ uint32_t add_if_less(uint32_t rank, uint64_t not_v, uint32_t mlo, uint32_t mhi) {
+    uint32_t t;
+    asm("{\n\t"
+        "add.cc.u32 %1, %4, %2;\n\t"
+        "addc.cc.u32 %1, %5, %3;\n\t"
+        "addc.u32 %0, %0, 0;\n\t"
+        "}"
+        : "+r"(rank), "=&r"(t)
+        : "r"((uint32_t)not_v), "r"((uint32_t)(not_v >> 32)), "r"(mlo), "r"(mhi));
+    return rank;
+}
+static constexpr int CELL_EMPTY = -1, CELL_QUEUED = -2;
+__global__ void __launch_bounds__(SEL_THREADS) i2r_select_small(I2RArgs a, int64_t M) {
+    __shared__ uint64_t buf[SEL_CAP];  // the staged pairs, complemented (see add_if_less)
+    __shared__ int s_off[SEL_CELLS + 1];
+    __shared__ int s_k[SEL_CELLS];         // median rank of the cell, or CELL_EMPTY / CELL_QUEUED
+    __shared__ uint32_t s_win[SEL_CELLS];  // the winner's global pixel index
+    const int tid = threadIdx.x;
+    const int64_t g0 = blockIdx.x * (int64_t)SEL_CELLS;
+    const int ncell = (int)min((int64_t)SEL_CELLS, M - g0);
+    if (tid <= ncell) s_off[tid] = a.bin_offset[g0 + tid];
     __syncthreads();
-    if (gbin >= M) return;
-    const int b = (int)(gbin / a.res2);
-    const int nreg = a.bin_count[gbin], nnan = a.nan_count[b];
-    const int cnt = nreg + nnan;  // (~angle_mask).sum(-1), img2refmap.py:28
-    const int64_t base = a.offsets[b];
-    if (cnt == 0 || cnt < a.min_points) {
-        write_cell(a, gbin, base, false, cnt, 0);
-        return;
+    const int run0 = s_off[0];
+    const int staged = min(s_off[ncell] - run0, SEL_CAP);
+    {
+        const uint64_t* __restrict__ src = reinterpret_cast<const uint64_t*>(a.pairs) + run0;
+        for (int e = tid; e < staged; e += SEL_THREADS) buf[e] = ~src[e];
     }
-    if (nnan > 0 || nreg > SMALL_MAX || a.reduce_mode != 0 || !staged) {
-        a.big_list[atomicAdd(a.big_count, 1)] = (int32_t)gbin;
-        return;
+    int b = 0, cnt = 0;
+    if (tid < ncell) {
+        b = (int)(g0 + tid) / a.res2;  // M < 2^31
+        const int off = s_off[tid] - run0, nreg = s_off[tid + 1] - s_off[tid], nnan = a.nan_count[b];
+        cnt = nreg + nnan;  // (~angle_mask).sum(-1), img2refmap.py:28
+        int k;
+        if (cnt == 0 || cnt < a.min_points) k = CELL_EMPTY;
+        else if (nnan > 0 || nreg > SEL_MAXN || a.reduce_mode != 0 || off + nreg > staged) k = CELL_QUEUED;
+        else k = (nreg - 1) >> 1;  // lower median, torch.nanmedian (:31); corrected below if some keys are NaN
+        s_k[tid] = k;
     }
-    uint64_t* seg = buf + (a.bin_offset[gbin] - run0);
-    int nvalid = 0;
-    for (int e = 0; e < nreg; ++e) nvalid += (uint32_t)(seg[e] >> 32) != KEY_NAN;
-    if (nvalid == 0) {
-        write_cell(a, gbin, base, false, cnt, 0);
-        return;
+    __syncthreads();
+    if (tid < ncell && s_k[tid] >= 0 && a.nankey_flag[b]) {
+        // NaN keys are the largest values, so rank (nvalid - 1) / 2 of the whole segment is the lower median of the
+        // valid members
+        const int off = s_off[tid] - run0, nreg = s_off[tid + 1] - s_off[tid];
+        int nvalid = 0;
+        for (int e = 0; e < nreg; ++e) nvalid += (uint32_t)(~buf[off + e] >> 32) != KEY_NAN;
+        s_k[tid] = nvalid ? (nvalid - 1) >> 1 : CELL_EMPTY;
     }
-    // NaN keys are the largest values, so rank (nvalid - 1) / 2 of the whole segment is the lower median of the valid
-    // members (torch.nanmedian, :31)
-    const uint64_t med = quickselect(seg, nreg, (nvalid - 1) >> 1);
-    write_cell(a, gbin, base, true, cnt, (int64_t)(uint32_t)med);
+    __syncthreads();
+    for (int e = tid; e < staged; e += SEL_THREADS) {
+        const uint64_t mine = ~buf[e];
+        const int c = ((uint32_t)mine >> PIX_BITS);
+        const int k = s_k[c];
+        if (k < 0) continue;
+        const int n = s_off[c + 1] - s_off[c];
+        const uint64_t* __restrict__ seg = buf + (s_off[c] - run0);
+        const uint32_t mlo = (uint32_t)mine, mhi = (uint32_t)(mine >> 32);
+        uint32_t rank = 0;
+        int f = 0;
+#pragma unroll 1
+        for (; f + 4 <= n; f += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rank = add_if_less(rank, seg[f + u], mlo, mhi);
+        }
+#pragma unroll 1
+        for (; f < n; ++f) rank = add_if_less(rank, seg[f], mlo, mhi);
+        if ((int)rank == k) s_win[c] = mlo & PIX_MASK;
+    }
+    __syncthreads();
+    if (tid < ncell) {
+        const int k = s_k[tid];
+        if (k == CELL_QUEUED) a.big_list[atomicAdd(a.big_count, 1)] = (int32_t)(g0 + tid);
+        else write_cell(a, g0 + tid, a.offsets[b], k >= 0, cnt, k >= 0 ? (int64_t)s_win[tid] : 0);
+    }
 }
 
 // one warp per queued cell
@@ -383,7 +451,7 @@ __global__ void __launch_bounds__(256) i2r_select_big(I2RArgs a) {
         const int b = (int)(gbin / a.res2);
         const int64_t base = a.offsets[b];
         CellView cv;
-        cv.nreg = a.bin_count[gbin];
+        cv.nreg = a.bin_offset[gbin + 1] - a.bin_offset[gbin];
         cv.seg = a.pairs + a.bin_offset[gbin];
         cv.nnan = a.nan_count[b];
         cv.nan_list = a.nan_list + base;
@@ -458,22 +526,26 @@ static int64_t pairs_per_pixel_bound(int res, float thr) {
 
 static size_t i2r_carve(I2RArgs& a, void* ws, int64_t total_n, int B, int res, float thr) {
     const int64_t M = (int64_t)B * res * res;
-    const int64_t nblocks = (M + SCAN_TILE - 1) / SCAN_TILE;
+    const int64_t nblocks = (M + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    const size_t npx = (size_t)(total_n > 0 ? total_n : 1);
     Carver c(ws);
-    a.bin_count = c.take<int32_t>(M);
-    a.cursor = c.take<int32_t>(M);  // contiguous with bin_count + nan_count + status for one memset
+    a.cnt_first = c.take<int32_t>(M + 1);  // the zeroed block: carved first and contiguous, one memset
+    a.cnt_other = c.take<int32_t>(M + 1);
+    a.cursor = c.take<int32_t>(M);
     a.nan_count = c.take<int32_t>(B);
+    a.nankey_flag = c.take<int32_t>(B);
     a.big_count = c.take<int32_t>(1);
     a.status = c.take<int32_t>(1);
-    const size_t zero_end = c.used();
-    a.bin_offset = c.take<int32_t>(M);
-    a.nan_list = c.take<int32_t>(total_n > 0 ? total_n : 1);
-    a.cell0 = c.take<uint32_t>(total_n > 0 ? total_n : 1);
+    a.bin_offset = c.take<int32_t>(M + 1);
+    a.nan_list = c.take<int32_t>(npx);
+    a.cell0 = c.take<uint32_t>(npx);
+    a.key0 = c.take<uint32_t>(npx);
+    a.rank0 = c.take<int32_t>(npx);
     a.big_list = c.take<int32_t>(M);
     a.block_sums = c.take<int32_t>(nblocks + 1);
     a.pair_capacity = total_n * pairs_per_pixel_bound(res, thr);
     a.pairs = c.take<uint2>(a.pair_capacity > 0 ? a.pair_capacity : 1);
-    (void)zero_end;
+    a.block_image = c.take<int32_t>((npx + 255) / 256 + HIST_PX);
     return c.used();
 }
 
@@ -497,6 +569,7 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
     DRM_REQUIRE(reduce_mode == 0 || reduce_mode == 1, "img2refmap: reduce_mode %d (0 = median, 1 = mean)", reduce_mode);
     DRM_REQUIRE(offsets && refmap && refmask && (total_n == 0 || (colors && geom)), "img2refmap: null pointer");
     const int64_t M = (int64_t)B * res * res;
+    DRM_REQUIRE(total_n <= (1ll << PIX_BITS), "img2refmap: %lld pixels in one call, at most 2^26 (split the batch)", (long long)total_n);
     DRM_REQUIRE(M < (1ll << 31), "img2refmap: B*res*res = %lld exceeds int32 cells", (long long)M);
     const int64_t per_px = pairs_per_pixel_bound(res, thr);
     if (total_n * per_px >= (1ll << 31)) {
@@ -520,25 +593,26 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
     a.min_points = min_points; a.reduce_mode = reduce_mode;
     a.refmap = refmap; a.refmask = refmask; a.counts = counts; a.sel_index = sel_index;
 
-    // bin_count, cursor, nan_count, big_count, status are carved first and contiguous (each 256-aligned)
-    const size_t zero_bytes = (size_t)((char*)a.bin_offset - (char*)a.bin_count);
-    DRM_CHECK_CUDA(cudaMemsetAsync(a.bin_count, 0, zero_bytes, st));
-    const int64_t nblocks = (M + SCAN_TILE - 1) / SCAN_TILE;
+    // cnt_first, cnt_other, cursor, nan_count, big_count, status are carved first and contiguous (each 256-aligned)
+    const size_t zero_bytes = (size_t)((char*)a.bin_offset - (char*)a.cnt_first);
+    DRM_CHECK_CUDA(cudaMemsetAsync(a.cnt_first, 0, zero_bytes, st));
+    const int64_t nblocks = (M + 1 + SCAN_TILE - 1) / SCAN_TILE;
     if (total_n > 0) {
-        const unsigned grid = (unsigned)((total_n + 255) / 256);
-        i2r_hist_pass<<<grid, 256, 0, st>>>(a);
+        const int64_t nblk = (total_n + 255) / 256;
+        i2r_block_image_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(offsets, B, nblk, a.block_image);
+        i2r_hist_pass<<<(unsigned)((nblk + HIST_PX - 1) / HIST_PX), 256, 0, st>>>(a);
     }
-    scan_tiles<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_count, a.bin_offset, a.block_sums, M);
+    scan_tiles<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.cnt_first, a.cnt_other, a.bin_offset, a.block_sums, M + 1);
     scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(a.block_sums, (int)nblocks);
-    scan_add<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_offset, a.block_sums, M);
+    scan_add<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_offset, a.block_sums, M + 1);
     if (total_n > 0) {
-        const unsigned grid = (unsigned)((total_n + 255) / 256);
-        i2r_scatter_pass<<<grid, 256, 0, st>>>(a);
+        const int64_t nquad = (total_n + SCATTER_PX - 1) / SCATTER_PX;
+        i2r_scatter_pass<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(a);
     }
-    i2r_select_small<<<(unsigned)((M + SELECT_THREADS - 1) / SELECT_THREADS), SELECT_THREADS, 0, st>>>(a, M);
+    i2r_select_small<<<(unsigned)((M + SEL_CELLS - 1) / SEL_CELLS), SEL_THREADS, 0, st>>>(a, M);
     i2r_select_big<<<148 * 4, 256, 0, st>>>(a);
     DRM_CHECK_CUDA(cudaGetLastError());
-    count_launches(total_n > 0 ? 7 : 5);
+    count_launches(total_n > 0 ? 8 : 5);
     return DRM_OK;
 }
 

@@ -54,7 +54,7 @@ def img2refmap_batch(colors: torch.Tensor, normals: torch.Tensor, offsets: torch
     L = _lib.lib()
     with torch.cuda.device(device):
         refmap = torch.empty((B, res, res, C), dtype=torch.float32, device=device)
-        refmask = torch.empty((B, res, res), dtype=torch.uint8, device=device)
+        refmask = torch.empty((B, res, res), dtype=torch.bool, device=device)  # the kernels store 0/1 bytes
         counts = torch.empty((B, res, res), dtype=torch.int32, device=device)
         sel = torch.empty((B, res, res), dtype=torch.int32, device=device)
         nbytes = L.drm_img2refmap_workspace_bytes(total_n, B, res, float(angle_threshold))
@@ -64,7 +64,7 @@ def img2refmap_batch(colors: torch.Tensor, normals: torch.Tensor, offsets: torch
                                     refmap.data_ptr(), refmask.data_ptr(), counts.data_ptr(), sel.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _stream_ptr(device)))
         ws.record_stream(torch.cuda.current_stream(device))
-    return refmap, refmask.bool(), counts, sel
+    return refmap, refmask, counts, sel
 
 
 def refmap_mask_make(colors: torch.Tensor, normals: torch.Tensor, res: int, angle_threshold: float = None,
