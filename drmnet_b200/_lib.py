@@ -77,6 +77,8 @@ def lib() -> ctypes.CDLL:
     L.drm_img2refmap_workspace_bytes.argtypes = [i64, i32, i32, f32]
     L.drm_img2refmap.restype = i32
     L.drm_img2refmap.argtypes = [vp, vp, i32, vp, i64, i32, i32, i32, f32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.drm_img2refmap_status.restype = i32
+    L.drm_img2refmap_status.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(ctypes.c_int32 * 2), vp]
     L.drm_refmap_postprocess.restype = i32
     L.drm_refmap_postprocess.argtypes = [vp, i32, i32, i32, f32, i32, vp, vp, vp]
     L.drm_mirmap2envmap.restype = i32
@@ -102,5 +104,5 @@ def check(code: int) -> None:
 EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_launch_count", "drm_render_workspace_bytes", "drm_render_refmaps",
                     "drm_render_refmaps_opts", "drm_render_default_options", "drm_render_status",
                     "drm_render_flat_workspace_bytes", "drm_render_refmaps_flat",
-                    "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_normals_to_thetaphi",
+                    "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_img2refmap_status", "drm_normals_to_thetaphi",
                     "drm_refmap_postprocess", "drm_mirmap2envmap", "drm_refmap_lookup", "drm_normalized_log"]

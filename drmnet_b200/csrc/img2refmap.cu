@@ -37,8 +37,9 @@ struct I2RArgs {
     int32_t* cursor;      // [M]   placement counter of those other pairs (pass 1)
     int32_t* nan_count;   // [B]
     int32_t* nan_list;    // [total_n]  (image b owns the slice starting at offsets[b])
-    int32_t* bin_offset;  // [M+1] exclusive scan of cnt_first + cnt_other; [M] = number of pairs
-    int32_t* block_sums;  // scan scratch
+    int32_t* bin_offset;  // [M+1] exclusive scan of cnt_first + cnt_other inside each tile of SCAN_TILE cells
+    int32_t* block_sums;  // [tiles] exclusive scan of the tile totals (seg_offset() adds the two)
+    int32_t* scan_ticket; // [1] counts finished scan tiles: the last one scans the tile totals
     uint2* pairs;         // (cell tag << 26 | global pixel index, key): one 64-bit load gives (key << 32) | tag | pixel,
                           // whose order inside a cell is the total order (key, pixel); tag = cell % SEL_CELLS
     uint32_t* cell0;      // [total_n] first cell of each pixel (CELL_NONE if none), bit 31 set if it has more cells
@@ -55,6 +56,13 @@ struct I2RArgs {
     int32_t* counts;
     int32_t* sel_index;
 };
+
+static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// first pair of cell g: the scan leaves tile-local prefixes in bin_offset and the tiles' own prefixes in block_sums
+__device__ __forceinline__ int seg_offset(const I2RArgs& a, int g) {
+    return a.bin_offset[g] + a.block_sums[g / SCAN_TILE];
+}
 
 // theta = acos(n . [0,1,0]), phi = atan2(n . [0,0,1], n . [-1,0,0]) with the dot products evaluated literally
 // (utils/transform.py:87-88 with normal=[0,1,0], tangent=[-1,0,0], binormal=cross=[0,0,1]); IEEE acosf/atan2f.
@@ -114,6 +122,16 @@ __device__ __forceinline__ bool axis_cells(const I2RArgs& a, float x, int& lo, i
     lo = max(__float2int_rd((x - a.thr) * a.inv_step - 0.5f), 0);
     hi = min(__float2int_rd((x + a.thr) * a.inv_step - 0.5f), a.res - 2) + 1;
     const float thr = a.thr, step = a.stepf;
+    if (hi - lo <= 2) {
+        // up to three candidates (any window narrower than a cell): tested side by side, no loop
+        const float f = (float)lo;  // (float)(lo + k) + 0.5f == f + (k + 0.5f) exactly
+        const bool p0 = hi >= lo && fabsf(__fsub_rn(__fmul_rn(f + 0.5f, step), x)) <= thr;
+        const bool p1 = hi > lo && fabsf(__fsub_rn(__fmul_rn(f + 1.5f, step), x)) <= thr;
+        const bool p2 = hi > lo + 1 && fabsf(__fsub_rn(__fmul_rn(f + 2.5f, step), x)) <= thr;
+        hi = p2 ? lo + 2 : p1 ? lo + 1 : lo;
+        lo = p0 ? lo : p1 ? lo + 1 : lo + 2;
+        return p0 || p1 || p2;
+    }
     while (lo <= hi && fabsf(__fsub_rn(__fmul_rn((float)lo + 0.5f, step), x)) > thr) ++lo;
     while (hi > lo && fabsf(__fsub_rn(__fmul_rn((float)hi + 0.5f, step), x)) > thr) --hi;
     return lo <= hi;
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256) i2r_scatter_pass(I2RArgs a) {
         }
     }
 #pragma unroll
-    for (int u = 0; u < SCATTER_PX; ++u) off[u] = c0[u] != CELL_NONE ? a.bin_offset[c0[u] & ~CELL_MULTI] : 0;
+    for (int u = 0; u < SCATTER_PX; ++u) off[u] = c0[u] != CELL_NONE ? seg_offset(a, (int)(c0[u] & ~CELL_MULTI)) : 0;
 #pragma unroll
     for (int u = 0; u < SCATTER_PX; ++u)
         if (c0[u] != CELL_NONE) place_pair(a, (int64_t)off[u] + rank[u], (int)(c0[u] & ~CELL_MULTI), (uint32_t)(p0 + u), key[u]);
@@ -250,14 +268,13 @@ __global__ void __launch_bounds__(256) i2r_scatter_pass(I2RArgs a) {
         for (int i = i0; i <= i1; ++i)
             for (int j = (i == i0 ? j0 + 1 : j0); j <= j1; ++j) {
                 const int g = img0 + i * a.res + j;
-                place_pair(a, (int64_t)a.bin_offset[g] + a.cnt_first[g] + atomicAdd(&a.cursor[g], 1), g, (uint32_t)p, key[u]);
+                place_pair(a, (int64_t)seg_offset(a, g) + a.cnt_first[g] + atomicAdd(&a.cursor[g], 1), g, (uint32_t)p, key[u]);
             }
     }
 }
 
-// ---- exclusive scan of cnt_first + cnt_other (3 small kernels; M + 1 <= B*res^2 + 1 ints) ----------------------------------------
-static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
+// ---- exclusive scan of cnt_first + cnt_other: ONE kernel.  Every CTA scans its tile of SCAN_TILE cells; the CTA that
+// finishes last (a ticket counter) scans the tile totals.  The consumers add the two levels (seg_offset).
 __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
     __shared__ int warp_sums[SCAN_THREADS / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -283,9 +300,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
     return wprefix + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int32_t* __restrict__ in, const int32_t* __restrict__ in2,
-                                                           int32_t* __restrict__ out, int32_t* __restrict__ block_sums,
-                                                           int64_t M) {
+__global__ void __launch_bounds__(SCAN_THREADS) i2r_scan_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ in2,
+                                                                int32_t* __restrict__ out, int32_t* block_sums,
+                                                                int32_t* ticket, int64_t M) {
+    __shared__ bool last;
     const int64_t start = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS], s = 0;
 #pragma unroll
@@ -300,28 +318,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles(const int32_t* __rest
         if (start + k < M) out[start + k] = ex;
         ex += v[k];
     }
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(int32_t* block_sums, int nblocks) {
-    int carry = 0;
-    for (int start = 0; start < nblocks; start += SCAN_THREADS) {
-        int i = start + threadIdx.x;
-        int v = i < nblocks ? block_sums[i] : 0;
-        int total;
-        int ex = block_exclusive_scan(v, total);
-        if (i < nblocks) block_sums[i] = carry + ex;
-        carry += total;
+    if (threadIdx.x == 0) {
+        block_sums[blockIdx.x] = total;
+        __threadfence();
+        last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
     }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ block_sums,
-                                                         int64_t M) {
-    const int add = block_sums[blockIdx.x];
-    const int64_t start = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-        if (start + k < M) out[start + k] += add;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nblocks = (int)gridDim.x;
+    int carry = 0;
+    for (int s0 = 0; s0 < nblocks; s0 += SCAN_THREADS) {
+        const int i = s0 + threadIdx.x;
+        const int t = i < nblocks ? __ldcg(&block_sums[i]) : 0;
+        int tot;
+        const int e = block_exclusive_scan(t, tot);
+        if (i < nblocks) block_sums[i] = carry + e;
+        carry += tot;
+    }
 }
 
 // ---- selection of the lower median under the total order (sum key, pixel index) ----------------------------------
@@ -357,9 +371,9 @@ __device__ __forceinline__ void write_cell(const I2RArgs& a, int64_t gbin, int64
 // distinct 64-bit values) and the one whose rank is the lower-median rank names the winner.  All lanes stay busy
 // whatever the cell sizes are; a warp's lanes belong to two or three neighbouring cells, so they read the same few
 // shared-memory words (broadcast).  The cells' outputs are then written by one thread per cell, coalesced.
-// Cells that do not fit (more than SEL_MAXN members, or a run beyond the staging buffer), cells with NaN-angle
-// members and the mean mode are queued for the warp-per-cell kernel.
-static constexpr int SEL_THREADS = 256, SEL_CAP = 3072, SEL_MAXN = 512;
+// When the 64 cells hold more pairs than the staging buffer they are taken in several batches.  Cells with more than
+// SEL_MAXN members, cells with NaN-angle members and the mean mode are queued for the warp-per-cell kernel.
+static constexpr int SEL_THREADS = 256, SEL_CAP = 3072, SEL_MAXN = 1024;
 
 // rank + (v < mine) for 64-bit values: v < mine exactly when mine + ~v (= mine - v - 1 mod 2^64) carries out, so the
 // comparison is one add-with-carry chain and its carry is added to the rank -- no predicates, no selects
@@ -384,53 +398,63 @@ __global__ void __launch_bounds__(SEL_THREADS) i2r_select_small(I2RArgs a, int64
     const int tid = threadIdx.x;
     const int64_t g0 = blockIdx.x * (int64_t)SEL_CELLS;
     const int ncell = (int)min((int64_t)SEL_CELLS, M - g0);
-    if (tid <= ncell) s_off[tid] = a.bin_offset[g0 + tid];
+    if (tid <= ncell) s_off[tid] = seg_offset(a, (int)(g0 + tid));
     __syncthreads();
-    const int run0 = s_off[0];
-    const int staged = min(s_off[ncell] - run0, SEL_CAP);
-    {
-        const uint64_t* __restrict__ src = reinterpret_cast<const uint64_t*>(a.pairs) + run0;
-        for (int e = tid; e < staged; e += SEL_THREADS) buf[e] = ~src[e];
-    }
     int b = 0, cnt = 0;
     if (tid < ncell) {
         b = (int)(g0 + tid) / a.res2;  // M < 2^31
-        const int off = s_off[tid] - run0, nreg = s_off[tid + 1] - s_off[tid], nnan = a.nan_count[b];
+        const int nreg = s_off[tid + 1] - s_off[tid], nnan = a.nan_count[b];
         cnt = nreg + nnan;  // (~angle_mask).sum(-1), img2refmap.py:28
         int k;
         if (cnt == 0 || cnt < a.min_points) k = CELL_EMPTY;
-        else if (nnan > 0 || nreg > SEL_MAXN || a.reduce_mode != 0 || off + nreg > staged) k = CELL_QUEUED;
+        else if (nnan > 0 || nreg > SEL_MAXN || a.reduce_mode != 0) k = CELL_QUEUED;
         else k = (nreg - 1) >> 1;  // lower median, torch.nanmedian (:31); corrected below if some keys are NaN
         s_k[tid] = k;
     }
-    __syncthreads();
-    if (tid < ncell && s_k[tid] >= 0 && a.nankey_flag[b]) {
-        // NaN keys are the largest values, so rank (nvalid - 1) / 2 of the whole segment is the lower median of the
-        // valid members
-        const int off = s_off[tid] - run0, nreg = s_off[tid + 1] - s_off[tid];
-        int nvalid = 0;
-        for (int e = 0; e < nreg; ++e) nvalid += (uint32_t)(~buf[off + e] >> 32) != KEY_NAN;
-        s_k[tid] = nvalid ? (nvalid - 1) >> 1 : CELL_EMPTY;
-    }
-    __syncthreads();
-    for (int e = tid; e < staged; e += SEL_THREADS) {
-        const uint64_t mine = ~buf[e];
-        const int c = ((uint32_t)mine >> PIX_BITS);
-        const int k = s_k[c];
-        if (k < 0) continue;
-        const int n = s_off[c + 1] - s_off[c];
-        const uint64_t* __restrict__ seg = buf + (s_off[c] - run0);
-        const uint32_t mlo = (uint32_t)mine, mhi = (uint32_t)(mine >> 32);
-        uint32_t rank = 0;
-        int f = 0;
-#pragma unroll 1
-        for (; f + 4 <= n; f += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) rank = add_if_less(rank, seg[f + u], mlo, mhi);
+    // the cells are taken in batches whose pairs fit the staging buffer: all of them at once unless they are large
+    for (int c0 = 0; c0 < ncell;) {
+        int c1 = ncell;
+        if (s_off[ncell] - s_off[c0] > SEL_CAP) {
+            c1 = c0 + 1;  // a cell beyond SEL_MAXN <= SEL_CAP is queued: staging a part of it is harmless
+            while (c1 < ncell && s_off[c1 + 1] - s_off[c0] <= SEL_CAP) ++c1;
         }
+        const int run0 = s_off[c0];
+        const int staged = min(s_off[c1] - run0, SEL_CAP);
+        __syncthreads();  // s_k written; the previous batch is done with buf
+        {
+            const uint64_t* __restrict__ src = reinterpret_cast<const uint64_t*>(a.pairs) + run0;
+            for (int e = tid; e < staged; e += SEL_THREADS) buf[e] = ~src[e];
+        }
+        __syncthreads();
+        if (tid >= c0 && tid < c1 && s_k[tid] >= 0 && a.nankey_flag[b]) {
+            // NaN keys are the largest values, so rank (nvalid - 1) / 2 of the whole segment is the lower median of the
+            // valid members
+            const int off = s_off[tid] - run0, nreg = s_off[tid + 1] - s_off[tid];
+            int nvalid = 0;
+            for (int e = 0; e < nreg; ++e) nvalid += (uint32_t)(~buf[off + e] >> 32) != KEY_NAN;
+            s_k[tid] = nvalid ? (nvalid - 1) >> 1 : CELL_EMPTY;
+        }
+        __syncthreads();
+        for (int e = tid; e < staged; e += SEL_THREADS) {
+            const uint64_t mine = ~buf[e];
+            const int c = ((uint32_t)mine >> PIX_BITS);
+            const int k = s_k[c];
+            if (k < 0) continue;
+            const int n = s_off[c + 1] - s_off[c];
+            const uint64_t* __restrict__ seg = buf + (s_off[c] - run0);
+            const uint32_t mlo = (uint32_t)mine, mhi = (uint32_t)(mine >> 32);
+            uint32_t rank = 0;
+            int f = 0;
 #pragma unroll 1
-        for (; f < n; ++f) rank = add_if_less(rank, seg[f], mlo, mhi);
-        if ((int)rank == k) s_win[c] = mlo & PIX_MASK;
+            for (; f + 4 <= n; f += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rank = add_if_less(rank, seg[f + u], mlo, mhi);
+            }
+#pragma unroll 1
+            for (; f < n; ++f) rank = add_if_less(rank, seg[f], mlo, mhi);
+            if ((int)rank == k) s_win[c] = mlo & PIX_MASK;
+        }
+        c0 = c1;
     }
     __syncthreads();
     if (tid < ncell) {
@@ -451,8 +475,8 @@ __global__ void __launch_bounds__(256) i2r_select_big(I2RArgs a) {
         const int b = (int)(gbin / a.res2);
         const int64_t base = a.offsets[b];
         CellView cv;
-        cv.nreg = a.bin_offset[gbin + 1] - a.bin_offset[gbin];
-        cv.seg = a.pairs + a.bin_offset[gbin];
+        cv.nreg = seg_offset(a, (int)gbin + 1) - seg_offset(a, (int)gbin);
+        cv.seg = a.pairs + seg_offset(a, (int)gbin);
         cv.nnan = a.nan_count[b];
         cv.nan_list = a.nan_list + base;
         cv.base = base;
@@ -536,6 +560,7 @@ static size_t i2r_carve(I2RArgs& a, void* ws, int64_t total_n, int B, int res, f
     a.nankey_flag = c.take<int32_t>(B);
     a.big_count = c.take<int32_t>(1);
     a.status = c.take<int32_t>(1);
+    a.scan_ticket = c.take<int32_t>(1);
     a.bin_offset = c.take<int32_t>(M + 1);
     a.nan_list = c.take<int32_t>(npx);
     a.cell0 = c.take<uint32_t>(npx);
@@ -602,9 +627,8 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
         i2r_block_image_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(offsets, B, nblk, a.block_image);
         i2r_hist_pass<<<(unsigned)((nblk + HIST_PX - 1) / HIST_PX), 256, 0, st>>>(a);
     }
-    scan_tiles<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.cnt_first, a.cnt_other, a.bin_offset, a.block_sums, M + 1);
-    scan_block_sums<<<1, SCAN_THREADS, 0, st>>>(a.block_sums, (int)nblocks);
-    scan_add<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.bin_offset, a.block_sums, M + 1);
+    i2r_scan_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(a.cnt_first, a.cnt_other, a.bin_offset, a.block_sums,
+                                                                a.scan_ticket, M + 1);
     if (total_n > 0) {
         const int64_t nquad = (total_n + SCATTER_PX - 1) / SCATTER_PX;
         i2r_scatter_pass<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(a);
@@ -612,7 +636,19 @@ extern "C" int drm_img2refmap(const float* colors, const float* geom, int input_
     i2r_select_small<<<(unsigned)((M + SEL_CELLS - 1) / SEL_CELLS), SEL_THREADS, 0, st>>>(a, M);
     i2r_select_big<<<148 * 4, 256, 0, st>>>(a);
     DRM_CHECK_CUDA(cudaGetLastError());
-    count_launches(total_n > 0 ? 8 : 5);
+    count_launches(total_n > 0 ? 6 : 3);
+    return DRM_OK;
+}
+
+extern "C" int drm_img2refmap_status(const void* workspace, int64_t total_n, int B, int res, float thr, int32_t* status,
+                                     void* cuda_stream) {
+    DRM_REQUIRE(workspace && status && B > 0 && res > 0 && total_n >= 0 && thr >= 0.f, "img2refmap_status: bad arguments");
+    I2RArgs a{};
+    i2r_carve(a, const_cast<void*>(workspace), total_n, B, res, thr);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DRM_CHECK_CUDA(cudaMemcpyAsync(&status[0], a.status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DRM_CHECK_CUDA(cudaMemcpyAsync(&status[1], a.big_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DRM_CHECK_CUDA(cudaStreamSynchronize(st));
     return DRM_OK;
 }
 

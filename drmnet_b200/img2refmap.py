@@ -7,6 +7,8 @@ device -- there is no CPU path.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -23,15 +25,45 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"{name} is on {t.device}: drmnet_b200 has no CPU path (CUDA tensors only)")
 
 
+MAX_PIXELS_PER_CALL = 1 << 26  # include/drmrender.h: a pair keeps its cell tag above a 26-bit pixel index
+
+
+def split_batch(offsets_host, max_pixels: int = MAX_PIXELS_PER_CALL):
+    """Image ranges [(b0, b1), ...] whose pixel totals fit one library call (host logic, no device work)."""
+    offs = [int(o) for o in offsets_host]
+    groups, b0 = [], 0
+    for b in range(len(offs) - 1):
+        if offs[b + 1] - offs[b] > max_pixels:
+            raise ValueError(f"image {b} has {offs[b + 1] - offs[b]} pixels; one image can hold at most {max_pixels}")
+        if offs[b + 1] - offs[b0] > max_pixels:
+            groups.append((b0, b))
+            b0 = b
+    groups.append((b0, len(offs) - 1))
+    return groups
+
+
 def img2refmap_batch(colors: torch.Tensor, normals: torch.Tensor, offsets: torch.Tensor, res: int,
                      angle_threshold: float, min_points: int = 0, *, thetaphi: torch.Tensor | None = None,
-                     reduce: str = "median"):
+                     reduce: str = "median", check_status: bool = False):
     """Segmented scatter of B images in one launch sequence.
 
     colors [total_n, C] fp32, normals [total_n, 3] fp32 (or ``thetaphi`` [total_n, 2]), offsets [B+1] int64 (image b
     owns rows offsets[b]:offsets[b+1]).  Returns (refmap [B,res,res,C] fp32, refmask [B,res,res] bool,
     counts [B,res,res] int32, sel_index [B,res,res] int32 image-local, -1 where empty).
+    ``check_status`` reads the library's status word back (one stream synchronisation) and raises if the pair buffer
+    overflowed; ``img2refmap_batch.last_status`` then holds (flags, cells on the warp-per-cell path).
     """
+    if isinstance(colors, torch.Tensor) and colors.dim() == 2 and colors.shape[0] > MAX_PIXELS_PER_CALL:
+        geom_all = thetaphi if thetaphi is not None else normals
+        offs_h = offsets.cpu().tolist()
+        parts = []
+        for b0, b1 in split_batch(offs_h, MAX_PIXELS_PER_CALL):
+            lo, hi = offs_h[b0], offs_h[b1]
+            sub = torch.as_tensor(offs_h[b0:b1 + 1], dtype=torch.int64) - lo
+            kw = dict(thetaphi=geom_all[lo:hi]) if thetaphi is not None else {}
+            parts.append(img2refmap_batch(colors[lo:hi], None if thetaphi is not None else geom_all[lo:hi], sub, res,
+                                          angle_threshold, min_points, reduce=reduce, check_status=check_status, **kw))
+        return tuple(torch.cat([p[i] for p in parts]) for i in range(4))
     _require_cuda(colors, "colors")
     geom = thetaphi if thetaphi is not None else normals
     _require_cuda(geom, "normals")
@@ -63,6 +95,13 @@ def img2refmap_batch(colors: torch.Tensor, normals: torch.Tensor, offsets: torch
                                     total_n, B, C, int(res), float(angle_threshold), int(min_points), mode,
                                     refmap.data_ptr(), refmask.data_ptr(), counts.data_ptr(), sel.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _stream_ptr(device)))
+        if check_status:
+            st = (ctypes.c_int32 * 2)()
+            _lib.check(L.drm_img2refmap_status(ws.data_ptr(), total_n, B, int(res), float(angle_threshold),
+                                               ctypes.byref(st), _stream_ptr(device)))
+            img2refmap_batch.last_status = (int(st[0]), int(st[1]))
+            if st[0] & 1:
+                raise RuntimeError("img2refmap: the (cell, pixel) pair buffer overflowed; outputs are invalid")
         ws.record_stream(torch.cuda.current_stream(device))
     return refmap, refmask, counts, sel
 

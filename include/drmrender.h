@@ -136,6 +136,12 @@ int drm_render_refmaps_flat(const float* env, int B, int He, int We,
  *   refmap     [B, res, res, C] fp32, zeros where empty;  refmask [B, res, res] uint8 (0/1)
  *   counts     [B, res, res] int32 members per cell (may be NULL);  sel_index [B, res, res] int32 image-local index
  *              of the selected pixel, -1 where empty or in mean mode (may be NULL)
+ * One call takes at most 2^26 pixels (total_n) -- a (cell, pixel) pair keeps its cell tag above a 26-bit pixel index;
+ * larger batches are split by the caller (drmnet_b200/img2refmap.py does).
+ *
+ * drm_img2refmap_status: after a call on the same workspace and arguments, status[0] = flags (bit 0: the pair buffer
+ *   overflowed -- cannot happen while workspace_bytes is the value drm_img2refmap_workspace_bytes returns; the outputs
+ *   are not to be used if it is set), status[1] = cells that took the warp-per-cell path.  Synchronises the stream.
  * ------------------------------------------------------------------------------------------------------------- */
 size_t drm_img2refmap_workspace_bytes(int64_t total_n, int B, int res, float thr);
 
@@ -143,6 +149,9 @@ int drm_img2refmap(const float* colors, const float* normals_or_thetaphi, int in
                    const int64_t* offsets, int64_t total_n, int B, int C, int res, float thr, int min_points,
                    int reduce_mode, float* refmap, uint8_t* refmask, int32_t* counts, int32_t* sel_index,
                    void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+int drm_img2refmap_status(const void* workspace, int64_t total_n, int B, int res, float thr, int32_t* status /* [2] */,
+                          void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Callers either side of the render.

@@ -121,3 +121,33 @@ def test_reference_error_behaviour():
         refmap_mask_make(c, c, 16)  # angle_threshold=None fails at the comparison (:27)
     with pytest.raises(TypeError):
         refmap_mask_make(c.double(), c, 16, 0.1)
+
+
+@pytest.mark.parametrize("res", [8, 16, 48])
+def test_cell_sizes_across_both_select_paths(res):
+    """Cells of ~800-1500 members (res 8: some beyond the staged select, warp-per-cell path), ~200 (res 16: staged in
+    several batches per CTA) and ~20 (res 48), with duplicated colours so that keys tie inside the cells; status clean."""
+    colors, normals = sphere_image_inputs(128, seed=11)
+    colors = np.round(colors * 8) / 8  # many equal channel sums: the order falls back to the pixel index
+    tp = normals_to_thetaphi(_gpu(normals)).cpu().numpy()
+    thr = np.pi / res / 2
+    out = img2refmap_batch(_gpu(colors), None, torch.tensor([0, len(colors)]), res, thr, thetaphi=_gpu(tp),
+                           check_status=True)
+    flags, n_big = img2refmap_batch.last_status
+    assert flags == 0 and (n_big > 0) == (res == 8), (flags, n_big)
+    o = img2refmap_oracle(colors, None, res, thr, thetaphi=tp)
+    for ours, ref in zip(out, o):
+        assert np.array_equal(ours[0].cpu().numpy(), ref)
+
+
+def test_batches_beyond_the_per_call_pixel_limit_are_split(golden_synth, monkeypatch):
+    import drmnet_b200.img2refmap as M
+    a = golden_synth["A_half_cell_res32"]
+    colors, tp = a["colors"], a["thetaphi_torch_cpu"]
+    offsets = [0, 0, 2500, 2500, 4000, 6000]
+    whole = _run(colors, tp, 32, float(a["thr"]), 0, thetaphi=True, offsets=offsets)
+    monkeypatch.setattr(M, "MAX_PIXELS_PER_CALL", 2600)
+    assert M.split_batch(offsets, 2600) == [(0, 3), (3, 4), (4, 5)]
+    parts = _run(colors, tp, 32, float(a["thr"]), 0, thetaphi=True, offsets=offsets)
+    for x, y in zip(whole, parts):
+        assert np.array_equal(x, y)

@@ -132,3 +132,13 @@ def test_gauss_legendre_nodes_nest_in_the_weight_intervals_of_coarser_orders():
                 for i in range(m):
                     assert edges[a] < xf[a * m + i] < edges[a + 1], (S, Sk, a, i)
             Sk //= 2
+
+
+def test_img2refmap_batches_split_at_the_per_call_pixel_limit():
+    from drmnet_b200.img2refmap import MAX_PIXELS_PER_CALL, split_batch
+    assert MAX_PIXELS_PER_CALL == 1 << 26  # include/drmrender.h
+    assert split_batch([0, 10, 20, 30], 100) == [(0, 3)]
+    assert split_batch([0, 60, 100, 150, 150, 260], 110) == [(0, 2), (2, 4), (4, 5)]
+    assert split_batch([0, 0, 0], 5) == [(0, 2)]
+    with pytest.raises(ValueError):
+        split_batch([0, 7], 5)
