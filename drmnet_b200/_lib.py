@@ -87,6 +87,10 @@ def lib() -> ctypes.CDLL:
     L.drm_refmap_lookup.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
     L.drm_normalized_log.restype = i32
     L.drm_normalized_log.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.drm_obsnet_condition.restype = i32
+    L.drm_obsnet_condition.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]
+    L.drm_normalized_log_apply.restype = i32
+    L.drm_normalized_log_apply.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp]
     L.drm_normals_to_thetaphi.restype = i32
     L.drm_normals_to_thetaphi.argtypes = [vp, i64, vp, vp]
     _lib = L
@@ -105,4 +109,5 @@ EXPORTED_SYMBOLS = ["drm_version", "drm_last_error", "drm_launch_count", "drm_re
                     "drm_render_refmaps_opts", "drm_render_default_options", "drm_render_status",
                     "drm_render_flat_workspace_bytes", "drm_render_refmaps_flat",
                     "drm_img2refmap_workspace_bytes", "drm_img2refmap", "drm_img2refmap_status", "drm_normals_to_thetaphi",
-                    "drm_refmap_postprocess", "drm_mirmap2envmap", "drm_refmap_lookup", "drm_normalized_log"]
+                    "drm_refmap_postprocess", "drm_mirmap2envmap", "drm_refmap_lookup", "drm_normalized_log",
+                    "drm_obsnet_condition", "drm_normalized_log_apply"]

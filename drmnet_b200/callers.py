@@ -14,19 +14,32 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .renderer import B200RefMapRenderer, render_batch
+from .renderer import B200RefMapRenderer, _slots, render_batch
 
 
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def rendering_refmaps(renderer: B200RefMapRenderer, envmaps: torch.Tensor, z: torch.Tensor,
-                      brdf_param_names: Optional[Sequence[str]] = None, view_from: Optional[torch.Tensor] = None,
+def rendering_refmaps(renderer: B200RefMapRenderer, envmaps, z: torch.Tensor,
+                      brdf_param_names: Optional[Sequence[str]] = None, view_from=None,
                       new_scene: bool = False) -> torch.Tensor:
-    """envmaps [B,He,We,3], z [L,B,P] -> [L,B,3,res,res]: the L BRDF vectors of sample b share envmap b and view b,
-    exactly the grouping of the reference's double loop (models/drmnet.py:680-691), in one batched launch."""
+    """envmaps [B,He,We,3] (a tensor, or a list of [He,We,3] tensors), z [L,B,P] -> [L,B,3,res,res]: the L BRDF vectors
+    of sample b share envmap b and view b, exactly the grouping of the reference's double loop
+    (models/drmnet.py:680-705), in one batched launch.  ``view_from`` is [B,3] or a list of B views.
+
+    Like the loop it replaces, the call leaves its mark on the stateful renderer when ``new_scene`` is false: parameters
+    that are not named come from the renderer's persistent BSDF, and afterwards the renderer holds the last envmap, the
+    last view and the last BRDF vector (utils/mitsuba3_utils.py:411-430 called with envmap/view only at list_idx 0)."""
     assert len(envmaps) == z.size(1)
+    if isinstance(envmaps, (list, tuple)):
+        if isinstance(envmaps[0], str):
+            # the reference's branch for names (models/drmnet.py:685-689) empties the list it iterates and cannot work;
+            # EXR reading is outside the render path
+            raise NotImplementedError("envmap names are not supported: pass the [He,We,3] tensors")
+        envmaps = torch.stack([torch.as_tensor(e) for e in envmaps])
+    if isinstance(view_from, (list, tuple)):
+        view_from = torch.stack([torch.as_tensor(v, dtype=torch.float32) for v in view_from])
     L, B = z.shape[0], z.shape[1]
     names = brdf_param_names or renderer.brdf_param_names
     device = envmaps.device
@@ -35,10 +48,26 @@ def rendering_refmaps(renderer: B200RefMapRenderer, envmaps: torch.Tensor, z: to
     else:
         view = view_from.to(device)
     zz = z.to(device).transpose(0, 1).reshape(B * L, -1)  # batch-major like the reference's iteration order
+    flip = renderer._new_scene_flip if new_scene else renderer._flip
+    if not new_scene:
+        # unnamed parameters keep the persistent scene's values (they cannot change inside the loop either)
+        z6 = renderer._bsdf.to(device).repeat(B * L, 1)
+        slots = _slots(names)
+        z6[:, slots] = zz[:, :len(slots)].float().clip(0, 1)
+        zz, names_arg = z6, None
+    else:
+        names_arg = names
     env_index = torch.arange(B, device=device).repeat_interleave(L)
-    out = render_batch(envmaps, zz, view.repeat_interleave(L, dim=0), env_index=env_index, brdf_param_names=names,
-                       res=renderer.refmap_res, footprint_S=renderer.footprint_S, alpha_min=renderer.alpha_min or 0.0,
-                       channel_first=True)
+    out = render_batch(envmaps, zz, view.repeat_interleave(L, dim=0), env_index=env_index, brdf_param_names=names_arg,
+                       flip=torch.full((B * L,), bool(flip), device=device), res=renderer.refmap_res,
+                       footprint_S=renderer.footprint_S, alpha_min=renderer.alpha_min or 0.0, channel_first=True)
+    if not new_scene:
+        renderer._envmap = envmaps[-1].to(renderer.device, torch.float32)
+        renderer._bsdf = zz[-1].detach().clone()
+        if view_from is not None:
+            renderer._view = view[-1].detach().float().cpu()
+    elif view_from is not None:
+        renderer._new_scene_view = view[-1].detach().float().cpu()
     return out.reshape(B, L, 3, renderer.refmap_res, renderer.refmap_res).transpose(0, 1).contiguous()
 
 
@@ -167,3 +196,64 @@ def normalized_log_transform(x: torch.Tensor, mask: torch.Tensor, lowerbound: fl
         _lib.check(_lib.lib().drm_normalized_log(x.data_ptr(), mask.data_ptr(), B, C, H, W, float(lowerbound),
                                                  out.data_ptr(), lmin.data_ptr(), lmax.data_ptr(), _stream(x.device)))
     return out, (lmin, lmax)
+
+
+def _nlog_apply(x: torch.Tensor, params, lowerbound: float, inverse: int, clamp_before_exp: float) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor: drmnet_b200 has no CPU path")
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    lmin, lmax = (p.to(x.device).float().reshape(-1).contiguous() for p in params)
+    if lmin.numel() != B or lmax.numel() != B:
+        # the reference asserts the parameters broadcast against x (dataset/basedataset.py:69)
+        raise AssertionError(f"{B} samples but {lmin.numel()} / {lmax.numel()} normalisation parameters")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().drm_normalized_log_apply(x.data_ptr(), lmin.data_ptr(), lmax.data_ptr(), B, C, H, W,
+                                                       float(lowerbound), inverse, float(clamp_before_exp or 0.0),
+                                                       out.data_ptr(), _stream(x.device)))
+    return out
+
+
+def normalized_log_apply(x: torch.Tensor, params, lowerbound: float = 1e-6) -> torch.Tensor:
+    """`ds.transform(x, dynamic_normalize=False)` for `0p1tom1p1_normalizedLogarithmic_lowerbound<lb>` with the parameters
+    (log10min [B], log10max [B]) of an earlier dynamic call -- LrK at models/obsnet.py:371 (dataset/basedataset.py:68-72)."""
+    return _nlog_apply(x, params, lowerbound, 0, 0.0)
+
+
+def normalized_log_rescale(y: torch.Tensor, params, clamp_before_exp: float = 0.0) -> torch.Tensor:
+    """`ds.rescale(y)` for the same chain (dataset/basedataset.py:83-110): back to linear radiance."""
+    return _nlog_apply(y, params, 0.0, 1, clamp_before_exp)
+
+
+def obsnet_condition(raw_refmap: torch.Tensor, raw_refmask: torch.Tensor, lowerbound: float = 1e-6,
+                     noisy_observe: float = 0.0, observe_noise: Optional[torch.Tensor] = None,
+                     padding_mode: str = "zeros", padding_noise: Optional[torch.Tensor] = None):
+    """ObsNet's conditioning from an observed refmap, one fused kernel (models/obsnet.py:672-691 with
+    cond_stage_key "raw_refmap"; the training path :368-370 is noisy_observe=0, padding "zeros").
+
+    raw_refmap [B,C,H,W], raw_refmask [B,H,W] bool/float.  Returns (cond [B,C,H,W], mask [B,1,H,W] float,
+    (log10min [B], log10max [B])).  The reference draws its noise with torch.randn_like; pass the tensors
+    (``observe_noise`` when noisy_observe > 0, ``padding_noise`` when padding_mode == "noise") or leave them None to
+    have them drawn here with torch.randn_like in the reference's order."""
+    if padding_mode not in ("zeros", "noise"):
+        raise NotImplementedError()  # models/obsnet.py:694-695
+    if not raw_refmap.is_cuda:
+        raise RuntimeError("raw_refmap must be a CUDA tensor: drmnet_b200 has no CPU path")
+    x = raw_refmap.contiguous().float()
+    B, C, H, W = x.shape
+    mask = raw_refmask.to(x.device).float().reshape(B, H, W).contiguous()
+    n1 = n2 = None
+    if noisy_observe > 0:
+        n1 = torch.randn_like(x) if observe_noise is None else observe_noise.to(x.device).float().contiguous()
+    if padding_mode == "noise":
+        n2 = torch.randn_like(x) if padding_noise is None else padding_noise.to(x.device).float().contiguous()
+    cond = torch.empty_like(x)
+    lmin = torch.empty(B, dtype=torch.float32, device=x.device)
+    lmax = torch.empty(B, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().drm_obsnet_condition(x.data_ptr(), mask.data_ptr(), B, C, H, W, float(lowerbound),
+                                                   float(noisy_observe), n1.data_ptr() if n1 is not None else None,
+                                                   n2.data_ptr() if n2 is not None else None, cond.data_ptr(),
+                                                   lmin.data_ptr(), lmax.data_ptr(), _stream(x.device)))
+    return cond, mask[:, None], (lmin, lmax)

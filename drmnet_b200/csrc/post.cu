@@ -170,9 +170,93 @@ __global__ void __launch_bounds__(POST_THREADS) normalized_log_kernel(const floa
         out[(size_t)n * C * P + e] = (log10f(fmaxf(xs[e], lowerbound)) - lmin) * inv * 2.f - 1.f;
 }
 
+// N4 remainder: ObsNet's conditioning (models/obsnet.py:672-691, training path :368-371).  One CTA per sample:
+// the dynamic normalisation of the raw refmap under its mask (above), then
+//   cond = t(raw) * mask;  cond = sigma * n1 + cond (noisy_observe > 0);  cond += (1 - mask) * n2 (padding "noise")
+// in that order, with the noise tensors drawn by the caller (torch.randn_like in the reference).
+__global__ void __launch_bounds__(POST_THREADS) obsnet_condition_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                                        int C, int P, float lowerbound, float sigma,
+                                                                        const float* __restrict__ n1, const float* __restrict__ n2,
+                                                                        float* __restrict__ cond, float* __restrict__ log10min_out,
+                                                                        float* __restrict__ log10max_out) {
+    __shared__ float sh[POST_THREADS / 32];
+    const int n = blockIdx.x;
+    const size_t base = (size_t)n * C * P;
+    const float* xs = x + base;
+    const float* ms = mask + (size_t)n * P;
+    float mx = -INFINITY;
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS) mx = fmaxf(mx, fmaxf(xs[e], lowerbound) * ms[e % P]);
+    mx = block_max(mx, sh);
+    float mn = -INFINITY;
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS) {
+        const float m = ms[e % P];
+        mn = fmaxf(mn, -(fmaxf(xs[e], lowerbound) * m + (1.f - m) * mx));
+    }
+    mn = -block_max(mn, sh);
+    const float lmax = log10f(mx), lmin = log10f(mn);
+    if (threadIdx.x == 0) {
+        if (log10min_out) log10min_out[n] = lmin;
+        if (log10max_out) log10max_out[n] = lmax;
+    }
+    const float inv = 1.f / (lmax - lmin);
+    for (int e = threadIdx.x; e < C * P; e += POST_THREADS) {
+        const float m = ms[e % P];
+        float c = ((log10f(fmaxf(xs[e], lowerbound)) - lmin) * inv * 2.f - 1.f) * m;
+        if (n1) c = sigma * n1[base + e] + c;
+        if (n2) c += (1.f - m) * n2[base + e];
+        cond[base + e] = c;
+    }
+}
+
+// the same transform with parameters fixed by an earlier dynamic call (dynamic_normalize=False, dataset/basedataset.py:68-72)
+// and its inverse, BaseDataset.rescale (:98-110): x -> (x + 1) / 2 -> 10 ^ min(x (max - min) + min, clamp)
+__global__ void normalized_log_apply_kernel(const float* __restrict__ x, const float* __restrict__ lmin,
+                                            const float* __restrict__ lmax, int64_t per_sample, int64_t total,
+                                            float lowerbound, int inverse, float clamp_before_exp, float* __restrict__ out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int n = (int)(e / per_sample);
+    const float a = lmin[n], b = lmax[n];
+    if (!inverse) {
+        out[e] = (log10f(fmaxf(x[e], lowerbound)) - a) / (b - a) * 2.f - 1.f;
+    } else {
+        float y = (x[e] + 1.f) / 2.f * (b - a) + a;
+        if (clamp_before_exp != 0.f) y = fminf(y, clamp_before_exp);
+        out[e] = powf(10.f, y);
+    }
+}
+
 }  // namespace drm
 
 using namespace drm;
+
+extern "C" int drm_obsnet_condition(const float* raw_refmap, const float* raw_refmask, int B, int C, int H, int W,
+                                    float lowerbound, float noisy_observe, const float* observe_noise,
+                                    const float* padding_noise, float* cond, float* log10min_out, float* log10max_out,
+                                    void* cuda_stream) {
+    DRM_REQUIRE(raw_refmap && raw_refmask && cond, "obsnet_condition: null pointer");
+    DRM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "obsnet_condition: sizes must be positive");
+    DRM_REQUIRE(!(noisy_observe > 0.f) || observe_noise, "obsnet_condition: noisy_observe > 0 needs observe_noise");
+    obsnet_condition_kernel<<<B, POST_THREADS, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        raw_refmap, raw_refmask, C, H * W, lowerbound, noisy_observe, noisy_observe > 0.f ? observe_noise : nullptr,
+        padding_noise, cond, log10min_out, log10max_out);
+    DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DRM_OK;
+}
+
+extern "C" int drm_normalized_log_apply(const float* x, const float* log10min, const float* log10max, int B, int C, int H,
+                                        int W, float lowerbound, int inverse, float clamp_before_exp, float* out,
+                                        void* cuda_stream) {
+    DRM_REQUIRE(x && log10min && log10max && out, "normalized_log_apply: null pointer");
+    DRM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "normalized_log_apply: sizes must be positive");
+    const int64_t per = (int64_t)C * H * W, total = per * B;
+    normalized_log_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        x, log10min, log10max, per, total, lowerbound, inverse, clamp_before_exp, out);
+    DRM_CHECK_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DRM_OK;
+}
 
 extern "C" int drm_refmap_lookup(const float* refmap, const float* normals, const int64_t* offsets, int64_t total_n,
                                  int B, int C, int H, int W, float* colors, void* cuda_stream) {

@@ -181,6 +181,21 @@ int drm_refmap_lookup(const float* refmap, const float* normals, const int64_t* 
 int drm_normalized_log(const float* x, const float* mask, int B, int C, int H, int W, float lowerbound,
                        float* out, float* log10min_out, float* log10max_out, void* cuda_stream);
 
+/* N4: ObsNet conditioning (models/obsnet.py:672-691; the training path :368-371 is the noise-free case): the transform
+ * above of raw_refmap [B, C, H, W] under raw_refmask [B, H, W] (float 0/1), then, in the reference's order,
+ *   cond = t(raw) * mask;  cond = noisy_observe * observe_noise + cond (if noisy_observe > 0);
+ *   cond += (1 - mask) * padding_noise (padding_mode "noise"; NULL = "zeros").
+ * The noise tensors [B, C, H, W] are drawn by the caller (torch.randn_like in the reference). */
+int drm_obsnet_condition(const float* raw_refmap, const float* raw_refmask, int B, int C, int H, int W,
+                         float lowerbound, float noisy_observe, const float* observe_noise, const float* padding_noise,
+                         float* cond, float* log10min_out, float* log10max_out, void* cuda_stream);
+
+/* N4: the same transform with the parameters of an earlier dynamic call (dynamic_normalize=False,
+ * dataset/basedataset.py:68-72; LrK at models/obsnet.py:371), inverse = 0; or BaseDataset.rescale (:98-110), inverse = 1:
+ * 10 ^ min((x + 1) / 2 * (max - min) + min, clamp_before_exp) (clamp_before_exp 0 = no clamp). */
+int drm_normalized_log_apply(const float* x, const float* log10min, const float* log10max, int B, int C, int H, int W,
+                             float lowerbound, int inverse, float clamp_before_exp, float* out, void* cuda_stream);
+
 /* angles only: [n,3] normals -> [n,2] (theta, phi), the arithmetic of utils/transform.py:84-89 at img2refmap.py:20 */
 int drm_normals_to_thetaphi(const float* normals, int64_t n, float* thetaphi, void* cuda_stream);
 

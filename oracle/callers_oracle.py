@@ -78,3 +78,34 @@ def normalized_log_oracle(x, mask, lowerbound=1e-6):
     log10min = np.log10((x * m + (1 - m) * linearmax).min(axis=(1, 2, 3), keepdims=True))
     y = (np.log10(x) - log10min) / (log10max - log10min)
     return y * 2 - 1, log10min.reshape(-1), log10max.reshape(-1)
+
+
+def normalized_log_apply_oracle(x, log10min, log10max, lowerbound=1e-6):
+    """dataset/basedataset.py:68-72 with stored parameters (dynamic_normalize=False), then `0p1tom1p1`."""
+    x = np.clip(np.asarray(x, dtype=np.float64), lowerbound, None)
+    a = np.asarray(log10min, dtype=np.float64).reshape(-1, 1, 1, 1)
+    b = np.asarray(log10max, dtype=np.float64).reshape(-1, 1, 1, 1)
+    return (np.log10(x) - a) / (b - a) * 2 - 1
+
+
+def normalized_log_rescale_oracle(y, log10min, log10max, clamp_before_exp=0.0):
+    """BaseDataset.rescale for the same chain (dataset/basedataset.py:83-110)."""
+    a = np.asarray(log10min, dtype=np.float64).reshape(-1, 1, 1, 1)
+    b = np.asarray(log10max, dtype=np.float64).reshape(-1, 1, 1, 1)
+    t = (np.asarray(y, dtype=np.float64) + 1) / 2 * (b - a) + a
+    if clamp_before_exp:
+        t = np.minimum(t, clamp_before_exp)
+    return 10.0 ** t
+
+
+def obsnet_condition_oracle(raw_refmap, raw_refmask, lowerbound=1e-6, noisy_observe=0.0, observe_noise=None,
+                            padding_noise=None):
+    """models/obsnet.py:672-691 for cond_stage_key "raw_refmap" (image_size equal to the refmap size)."""
+    t, lmin, lmax = normalized_log_oracle(raw_refmap, raw_refmask, lowerbound)
+    m = np.asarray(raw_refmask, dtype=np.float64).reshape(t.shape[0], 1, t.shape[2], t.shape[3])
+    cond = t * m
+    if noisy_observe > 0:
+        cond = noisy_observe * np.asarray(observe_noise, dtype=np.float64) + cond
+    if padding_noise is not None:
+        cond = cond + (1 - m) * np.asarray(padding_noise, dtype=np.float64)
+    return cond, lmin, lmax

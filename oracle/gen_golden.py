@@ -160,6 +160,44 @@ def callers_golden():
     blob["nlog_out"] = ds2.transform(y, dynamic_normalize=True, mask=mask).numpy()
     blob["nlog_min"] = ds2.Logarithmic_params[0].reshape(-1).numpy()
     blob["nlog_max"] = ds2.Logarithmic_params[1].reshape(-1).numpy()
+    # the same chain with stored parameters (dynamic_normalize=False, LrK at models/obsnet.py:371) and its inverse
+    z = torch.exp(2.0 * torch.randn(4, 3, 16, 16, generator=g))
+    blob["nlog_fixed_in"] = z.numpy()
+    blob["nlog_fixed_out"] = ds2.transform(z, dynamic_normalize=False, mask=mask).numpy()
+    w = torch.rand(4, 3, 16, 16, generator=g) * 2.4 - 1.2
+    blob["nlog_rescale_in"] = w.numpy()
+    blob["nlog_rescale_out"] = ds2.rescale(w).numpy()
+    ds3 = BaseDataset(size=16, transform_func="0p1tom1p1_normalizedLogarithmic_lowerbound1e-6", clamp_before_exp=0.5)
+    ds3.Logarithmic_params = ds2.Logarithmic_params
+    blob["nlog_rescale_clamped_out"] = ds3.rescale(w).numpy()
+    # ObsNet.get_cond_for_predict (models/obsnet.py:663-695): models/obsnet.py cannot be imported here either, so the
+    # source lines are executed with a stand-in `self`; torch.randn_like is wrapped to record the noise it drew
+    osrc = (REF / "models" / "obsnet.py").read_text().splitlines()[662:695]
+    assert osrc[0].strip() == "if self.model.conditioning_key is not None:" and "raise NotImplementedError()" in osrc[-1], osrc
+    drawn = []
+
+    class _T:  # torch with a recording randn_like
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def randn_like(t):
+            n = torch.randn(t.shape, generator=g)
+            drawn.append(n)
+            return n
+
+    for tag, sigma, padding in (("plain", 0.0, "zeros"), ("noisy", 0.05, "noise")):
+        drawn.clear()
+        me = types.SimpleNamespace(model=types.SimpleNamespace(conditioning_key="concat"), cond_stage_key="raw_refmap",
+                                   ds=BaseDataset(size=16, transform_func="0p1tom1p1_normalizedLogarithmic_lowerbound1e-6"),
+                                   noisy_observe=sigma, cond_stage_trainable=True, image_size=16, padding_mode=padding)
+        ns = {"torch": _T(), "self": me, "batch": {"raw_refmap": y.clone(), "raw_refmask": mask[:, 0].clone()}, "bs": None,
+              "force_c_encode": False}
+        exec(textwrap.dedent("\n".join(osrc)), ns)
+        blob[f"cond_{tag}"] = ns["cond"].numpy()
+        blob[f"cond_{tag}_mask"] = ns["mask"].numpy()
+        for i, n in enumerate(drawn):
+            blob[f"cond_{tag}_noise{i}"] = n.numpy()
     np.savez_compressed(OUT / "callers_ref.npz", **blob)
 
 

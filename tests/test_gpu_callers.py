@@ -9,6 +9,8 @@ from drmnet_b200.synth import BRDF_PARAM_NAMES, Z0, sample_brdf, sample_view, sc
 from oracle.callers_oracle import mirmap2envmap_oracle, postprocess_oracle
 from oracle.render_oracle import rel_l2
 
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -155,3 +157,80 @@ def test_round_trip_render_then_mirmap2envmap_recovers_the_envmap():
     assert ok < 0.1, ok
     for wrong in (env.flip(1), env.flip(0), torch.roll(env, 64, dims=1)):
         assert rel_l2(rec[front].cpu().numpy(), wrong[front].cpu().numpy()) > 3 * ok
+
+
+def test_obsnet_condition_matches_the_reference_lines():
+    """N4: the fused conditioning kernel and the fixed-parameter transform / rescale against goldens produced by the
+    reference's own code (oracle/gen_golden.py callers_golden: models/obsnet.py:663-695, dataset/basedataset.py:56-110),
+    and against the fp64 oracle on a refmap-sized batch."""
+    from drmnet_b200.callers import normalized_log_apply, normalized_log_rescale, obsnet_condition
+    from oracle.callers_oracle import obsnet_condition_oracle
+    g = np.load(GOLDEN / "callers_ref.npz")
+    raw, mask = torch.from_numpy(g["nlog_in"]).to(DEV), torch.from_numpy(g["nlog_mask"][:, 0]).to(DEV)
+    cond, m, (lmin, lmax) = obsnet_condition(raw, mask)
+    assert np.allclose(cond.cpu().numpy(), g["cond_plain"], rtol=2e-5, atol=2e-5)
+    assert np.array_equal(m.cpu().numpy(), g["cond_plain_mask"]) and m.shape == (4, 1, 16, 16)
+    assert np.allclose(lmin.cpu().numpy(), g["nlog_min"], atol=2e-6) and np.allclose(lmax.cpu().numpy(), g["nlog_max"], atol=2e-6)
+    cond, _, _ = obsnet_condition(raw, mask, noisy_observe=0.05, observe_noise=torch.from_numpy(g["cond_noisy_noise0"]),
+                                  padding_mode="noise", padding_noise=torch.from_numpy(g["cond_noisy_noise1"]))
+    assert np.allclose(cond.cpu().numpy(), g["cond_noisy"], rtol=2e-5, atol=2e-5)
+    # LrK with the raw refmap's parameters (models/obsnet.py:371), and the way back
+    t = normalized_log_apply(torch.from_numpy(g["nlog_fixed_in"]).to(DEV), (lmin, lmax))
+    assert np.allclose(t.cpu().numpy(), g["nlog_fixed_out"], rtol=2e-5, atol=2e-5)
+    w = torch.from_numpy(g["nlog_rescale_in"]).to(DEV)
+    assert np.allclose(normalized_log_rescale(w, (lmin, lmax)).cpu().numpy(), g["nlog_rescale_out"], rtol=3e-5)
+    assert np.allclose(normalized_log_rescale(w, (lmin, lmax), 0.5).cpu().numpy(), g["nlog_rescale_clamped_out"], rtol=3e-5)
+    back = normalized_log_rescale(t, (lmin, lmax))
+    assert np.allclose(back.cpu().numpy(), np.clip(g["nlog_fixed_in"], 1e-6, None), rtol=1e-4)
+    # refmap-sized batch against the oracle; drawn-here noise follows torch's generator
+    gen = torch.Generator().manual_seed(8)
+    x = torch.exp(torch.randn(6, 3, 128, 128, generator=gen) * 2)
+    mk = torch.rand(6, 128, 128, generator=gen) > 0.5
+    n1, n2 = torch.randn(6, 3, 128, 128, generator=gen), torch.randn(6, 3, 128, 128, generator=gen)
+    cond, _, _ = obsnet_condition(x.to(DEV), mk.to(DEV), noisy_observe=0.1, observe_noise=n1, padding_mode="noise",
+                                  padding_noise=n2)
+    ref, _, _ = obsnet_condition_oracle(x.numpy(), mk.numpy(), noisy_observe=0.1, observe_noise=n1.numpy(),
+                                        padding_noise=n2.numpy())
+    assert np.abs(cond.cpu().numpy() - ref).max() < 3e-5
+    torch.manual_seed(3)
+    a = obsnet_condition(x.to(DEV), mk.to(DEV), noisy_observe=0.1, padding_mode="noise")[0]
+    torch.manual_seed(3)
+    e1 = torch.randn_like(x.to(DEV)); e2 = torch.randn_like(x.to(DEV))
+    b = obsnet_condition(x.to(DEV), mk.to(DEV), noisy_observe=0.1, observe_noise=e1, padding_mode="noise", padding_noise=e2)[0]
+    assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError):
+        obsnet_condition(x.to(DEV), mk.to(DEV), padding_mode="reflect")
+    with pytest.raises(AssertionError):
+        normalized_log_apply(x.to(DEV), (lmin, lmax))
+
+
+def test_rendering_refmaps_list_inputs_partial_names_and_state():
+    """`[envmap]` / `[view_from]` lists as models/drmnet.py:943-952 passes them, a partial parameter list whose
+    unnamed slots come from the persistent scene, and the renderer's state after the call -- all equal to the loop of
+    stateful `rendering` calls that DRMNet.rendering_refmaps runs (models/drmnet.py:694-703)."""
+    res = 16
+    env = torch.from_numpy(synthetic_envmap(64, 128, seed=71)).to(DEV)
+    view = sample_view(71)
+
+    def fresh():
+        r = B200RefMapRenderer(refmap_res=res, spp=256, envmap_size=(64, 128), denoise="simple",
+                               brdf_param_names=BRDF_PARAM_NAMES, footprint_S=2)
+        # a first render leaves non-default metallic / specular in the persistent scene
+        r.rendering(torch.tensor([0.7, 0.6, 0.5, 0.4, 0.35, 0.6]), BRDF_PARAM_NAMES, envmap=env, channel_first=True)
+        return r
+
+    names = ["base_color.value.R", "base_color.value.G", "base_color.value.B", "roughness.value"]
+    z = torch.tensor([[[0.9, 0.8, 0.7, 0.3]], [[0.2, 0.3, 0.4, 0.6]]])  # [L=2, B=1, 4]
+    a, b = fresh(), fresh()
+    loop = torch.stack([a.rendering(z[i, 0], names, envmap=env if i == 0 else None, view_from=view if i == 0 else None,
+                                    channel_first=True) for i in range(2)])[:, None]
+    batched = rendering_refmaps(b, [env], z, brdf_param_names=names, view_from=[view])
+    assert batched.shape == (2, 1, 3, res, res)
+    assert rel_l2(batched.cpu().numpy(), loop.cpu().numpy()) < 5e-6
+    assert torch.equal(a._bsdf.cpu(), b._bsdf.cpu()) and torch.equal(a._view, b._view) and torch.equal(a._envmap, b._envmap)
+    # and the next stateful render continues from the same scene
+    nxt = torch.tensor([0.5])
+    assert torch.equal(a.rendering(nxt, ["roughness.value"], channel_first=True),
+                       b.rendering(nxt, ["roughness.value"], channel_first=True))
+    with pytest.raises(NotImplementedError):
+        rendering_refmaps(b, ["name"], z)

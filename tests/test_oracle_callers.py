@@ -77,3 +77,26 @@ def test_normalized_log_oracle_matches_torch_formulas():
     ours, lmin, lmax = normalized_log_oracle(x.numpy(), mask.numpy())
     assert np.allclose(ours, ref.numpy(), rtol=1e-5, atol=1e-5)
     assert np.allclose(lmin, log10min.reshape(-1).numpy(), atol=1e-6) and np.allclose(lmax, log10max.reshape(-1).numpy(), atol=1e-6)
+
+
+def test_obsnet_condition_oracles_match_reference_code():
+    """golden: BaseDataset.transform with stored parameters, BaseDataset.rescale (with and without clamp_before_exp), and
+    the source lines models/obsnet.py:663-695 (get_cond_for_predict, cond_stage_key 'raw_refmap') executed as they stand
+    with the noise they drew recorded -- the plain case and noisy_observe 0.05 + padding 'noise'."""
+    from oracle.callers_oracle import (normalized_log_apply_oracle, normalized_log_rescale_oracle,
+                                       obsnet_condition_oracle)
+    g = np.load(GOLDEN / "callers_ref.npz")
+    lmin, lmax = g["nlog_min"], g["nlog_max"]
+    assert np.allclose(normalized_log_apply_oracle(g["nlog_fixed_in"], lmin, lmax), g["nlog_fixed_out"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(normalized_log_rescale_oracle(g["nlog_rescale_in"], lmin, lmax), g["nlog_rescale_out"], rtol=2e-5)
+    assert np.allclose(normalized_log_rescale_oracle(g["nlog_rescale_in"], lmin, lmax, 0.5), g["nlog_rescale_clamped_out"],
+                       rtol=2e-5)
+    assert g["nlog_rescale_clamped_out"].max() <= 10 ** 0.5 * (1 + 1e-6) < g["nlog_rescale_out"].max()
+    cond, a, b = obsnet_condition_oracle(g["nlog_in"], g["nlog_mask"])
+    assert np.allclose(cond, g["cond_plain"], rtol=1e-5, atol=1e-5) and np.allclose(a, lmin, atol=1e-6)
+    assert np.array_equal(g["cond_plain_mask"], g["nlog_mask"].astype(np.float32))
+    cond, _, _ = obsnet_condition_oracle(g["nlog_in"], g["nlog_mask"], noisy_observe=0.05,
+                                         observe_noise=g["cond_noisy_noise0"], padding_noise=g["cond_noisy_noise1"])
+    assert np.allclose(cond, g["cond_noisy"], rtol=1e-5, atol=1e-5)
+    outside = ~np.broadcast_to(g["nlog_mask"], cond.shape)
+    assert np.allclose(cond[outside], (0.05 * g["cond_noisy_noise0"] + g["cond_noisy_noise1"])[outside], atol=1e-6)
