@@ -3,13 +3,21 @@
 // Replaces refmap_mask_make (reference utils/img2refmap.py:6-37) and the xyz2thetaphi call inside it
 // (utils/transform.py:84-89).  The reference tests every (cell, pixel) pair (O(res^2 n), [512,n,2] temporaries);
 // here each pixel generates only the cells whose fp32 window predicate it can satisfy, the (cell, pixel) pairs are
-// counting-sorted by cell (histogram -> exclusive scan -> scatter), and one warp per cell selects the lower median
-// under the total order (channel-sum, pixel index).  Integer atomics only place pairs inside a cell's segment; the
-// selection is order-independent, so every output is bit-exact and run-to-run deterministic.
+// counting-sorted by cell and the lower median under the total order (channel-sum, pixel index) is selected per cell.
+// Integer atomics only place pairs inside a cell's segment; the selection is order-independent, so every output is
+// bit-exact and run-to-run deterministic.
 //
-// HBM-bound integer/compare work: no tensor cores.  Traffic per image: normals and colours are read once (the first
-// pass leaves each pixel's cell id for the second), 8 B per pair written and read once, 4 int32 per cell.  Atomics are
-// aggregated per warp (__match_any_sync): raster-ordered pixels of an image mostly share their neighbours' cell.
+//   pass 0  i2r_hist_pass     normals + colours read once: angles, window, sum key; the histogram atomic's return value
+//                             is the pixel's rank inside its first cell -> (cell, key, rank) per pixel, 12 B
+//   scan    i2r_scan_kernel   one kernel, two-level exclusive scan of the cell counts
+//   pass 1  i2r_scatter_pass  pure placement pairs[offset(cell) + rank] = (tag | pixel, key): no atomics, no search
+//                             (pixels with several cells -- windows wider than a cell -- recompute their window here)
+//   select  i2r_select_small  64 cells per CTA staged in shared memory, element-parallel rank counting
+//           i2r_select_big    warp per cell: cells above 1024 members, NaN-angle members, mean mode
+//
+// HBM-bound integer/compare work by its bytes (24 B per pixel in, 13 B per cell out), no tensor cores; what limits the
+// kernels today is instruction issue (acosf/atan2f and the window tests in pass 0, the rank counting in the select) and
+// the L2 transaction rate of the 8-byte scattered stores in pass 1 -- see DESIGN.md.
 #include <math.h>
 
 #include "common.cuh"
@@ -379,7 +387,7 @@ static constexpr int SEL_THREADS = 256, SEL_CAP = 3072, SEL_MAXN = 1024;
 // comparison is one add-with-carry chain and its carry is added to the rank -- no predicates, no selects
 // (the staging buffer holds ~v)
 __device__ __forceinline__ uint32_t add_if_less(uint32_t rank, uint64_t not_v, uint32_t mlo, uint32_t mhi) {
-    uint32_t t;
+    [[maybe_unused]] uint32_t t;
     asm("{\n\t"
         "add.cc.u32 %1, %4, %2;\n\t"
         "addc.cc.u32 %1, %5, %3;\n\t"

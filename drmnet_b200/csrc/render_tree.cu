@@ -750,22 +750,31 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
             a2 += nd.mult * (cB.x + cB.y);
             n1 = 0;
         };
+        // Staged texels, two per iteration like the records: texels 2j, 2j+1 sit at buf0[4 j .. 4 j + 3] as
+        // (hx0,hx1,hy0,hy1) (hz0,hz1,2vh0,2vh1) (wR0,wR1,wG0,wG1) (wB0,wB1,-,-).
+        const f2 NVp = F2(nd.nv);
         auto eval0 = [&]() {
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll 2
-            for (int i = 0; i < n0; ++i) {
-                const float4 h = buf0[2 * i], w = buf0[2 * i + 1];
-                const float ex = nd.nx - h.x, ey = nd.ny - h.y, ez = nd.nz - h.z;
-                const float u2 = ex * ex + ey * ey + ez * ez;  // 2 (1 - n.h), no cancellation
-                const float nh = 1.f - 0.5f * u2;
-                const float xc = fmaxf(h.w * nh - nd.nv, 0.f);  // n.d = |v+d| n.h - n.v
-                const float sin2 = u2 * (1.f - 0.25f * u2);
-                const float q = 1.f + sin2 * rc.inv_a2m1;
-                const float sq = fast_sqrt(xc * xc * rc.one_m_a2 + alpha2);
-                const float ws = xc * fast_rcp(q * q * (xc + sq));
-                b0 += ws * w.x; b1 += ws * w.y; b2 += ws * w.z;
+            if (n0 & 1) {  // pad the last pair with a texel of zero weight
+                float* s = reinterpret_cast<float*>(buf0 + (n0 >> 1) * 4) + 1;
+                if (lane < 7) s[lane * 2] = lane < 3 ? (lane == 0 ? nd.nx : lane == 1 ? nd.ny : nd.nz) : 0.f;
+                __syncwarp();
             }
-            a0 += nd.mult * b0; a1 += nd.mult * b1; a2 += nd.mult * b2;
+            const int np = (n0 + 1) >> 1;
+            f2 bR = F2(0.f), bG = F2(0.f), bB = F2(0.f);
+#pragma unroll 2
+            for (int j = 0; j < np; ++j) {
+                const float4 v0 = buf0[4 * j], v1 = buf0[4 * j + 1], v2 = buf0[4 * j + 2], v3 = buf0[4 * j + 3];
+                const f2 ex = sub2(NX, lo(v0)), ey = sub2(NY, hi(v0)), ez = sub2(NZ, lo(v1));
+                const f2 u2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));  // 2 (1 - n.h), no cancellation
+                const f2 nh = fma2(u2, F2(-0.5f), F2(1.f));
+                const f2 xc = max2(sub2(mul2(hi(v1), nh), NVp), 0.f);   // n.d = |v+d| n.h - n.v
+                const f2 sin2 = mul2(u2, fma2(u2, F2(-0.25f), F2(1.f)));
+                const f2 q = fma2(sin2, CI, F2(1.f));
+                const f2 sq = sqrt2(fma2(mul2(xc, xc), OMA, A2));
+                const f2 ws = mul2(xc, rcp2(mul2(mul2(q, q), add2(xc, sq))));
+                bR = fma2(ws, lo(v2), bR); bG = fma2(ws, hi(v2), bG); bB = fma2(ws, lo(v3), bB);
+            }
+            a0 += nd.mult * (bR.x + bR.y); a1 += nd.mult * (bG.x + bG.y); a2 += nd.mult * (bB.x + bB.y);
             n0 = 0;
         };
 
@@ -932,9 +941,10 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
                         s[40] = vmu; s[42] = vx * svx + vy * svy + vz * svz;
                         s[44] = svx; s[46] = svy; s[48] = svz; s[50] = 0.f;
                     } else {
-                        float4* s = buf0 + (n0 + __popc(m0 & ((1u << lane) - 1u))) * 2;
-                        s[0] = make_float4(h[0], h[1], h[2], 2.f * vh);
-                        s[1] = make_float4(w3[0], w3[1], w3[2], 0.f);
+                        const int slot = n0 + __popc(m0 & ((1u << lane) - 1u));
+                        float* s = reinterpret_cast<float*>(buf0 + (slot >> 1) * 4) + (slot & 1);
+                        s[0] = h[0]; s[2] = h[1]; s[4] = h[2]; s[6] = 2.f * vh;
+                        s[8] = w3[0]; s[10] = w3[1]; s[12] = w3[2];
                     }
                 }
                 n1 += __popc(m1);

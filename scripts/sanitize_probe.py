@@ -6,7 +6,8 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 import torch
-from drmnet_b200.callers import mirmap2envmap, normalized_log_transform, refmap_lookup, refmap_postprocess
+from drmnet_b200.callers import (mirmap2envmap, normalized_log_apply, normalized_log_rescale, normalized_log_transform,
+                                  obsnet_condition, refmap_lookup, refmap_postprocess)
 from drmnet_b200.img2refmap import img2refmap_batch
 from drmnet_b200.renderer import render_batch
 from drmnet_b200.synth import Z0, sphere_image_inputs, synthetic_envmap
@@ -28,11 +29,23 @@ print("auto", float(a.mean()), "flat S=3", float(b.mean()))
 c, n = sphere_image_inputs(24, seed=2)
 offs = torch.tensor([0, len(c) // 2, len(c)], dtype=torch.int64, device=dev)
 for mode in ("median", "mean"):
-    r = img2refmap_batch(torch.from_numpy(c).to(dev), torch.from_numpy(n).to(dev), offs, 16, float(np.pi / 32), reduce=mode)
-    print("img2refmap", mode, int(r[1].sum()))
+    r = img2refmap_batch(torch.from_numpy(c).to(dev), torch.from_numpy(n).to(dev), offs, 16, float(np.pi / 32), reduce=mode,
+                         check_status=True)
+    print("img2refmap", mode, int(r[1].sum()), img2refmap_batch.last_status)
+# windows wider than a cell (several cells per pixel), cells larger than the staging buffer (batched select, warp-per-cell path)
+for res, thr in ((24, 0.2), (4, float(np.pi / 8))):
+    r = img2refmap_batch(torch.from_numpy(c).to(dev), torch.from_numpy(n).to(dev), offs, res, thr, check_status=True)
+    print("img2refmap res", res, "thr", round(thr, 3), int(r[1].sum()), img2refmap_batch.last_status)
+c2, n2 = sphere_image_inputs(96, seed=4)
+r = img2refmap_batch(torch.from_numpy(c2).to(dev), torch.from_numpy(n2).to(dev), torch.tensor([0, len(c2)]), 16, float(np.pi / 32),
+                     check_status=True)
+print("img2refmap ~110 px per cell", int(r[1].sum()), img2refmap_batch.last_status)
 st = torch.rand(3, 2, 3, 16, 16, device=dev)
 print("post", float(refmap_postprocess(st)[0].mean()))
 print("warp", float(mirmap2envmap(st[0], (16, 32)).mean()))
 print("lookup", float(refmap_lookup(st[0, :1], torch.from_numpy(n).to(dev)).mean()))
-print("nlog", float(normalized_log_transform(st[0] + 0.1, torch.ones(2, 1, 16, 16, device=dev))[0].mean()))
+t, prm = normalized_log_transform(st[0] + 0.1, torch.ones(2, 1, 16, 16, device=dev))
+print("nlog", float(t.mean()), float(normalized_log_rescale(normalized_log_apply(st[1] + 0.1, prm), prm).mean()))
+print("cond", float(obsnet_condition(st[0] + 0.1, torch.rand(2, 16, 16, device=dev) > 0.5, noisy_observe=0.1,
+                                     padding_mode="noise")[0].mean()))
 torch.cuda.synchronize()
