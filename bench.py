@@ -419,9 +419,21 @@ def main():
         else:
             end = ev[-1]
         barrier()
+    launches = L.drm_launch_count() - launches0
+    clock_info = clocks.summary()
+    if clock_info["samples"] < 2:
+        # the timed region was shorter than nvidia-smi's sampling period: keep the same load running until it has sampled
+        with ClockSampler(local_rank) as clocks2:
+            t_end = time.perf_counter() + 0.9
+            while time.perf_counter() < t_end:
+                step()
+                torch.cuda.synchronize()
+            if gather is not None:
+                gather.result()
+        clock_info = dict(clocks2.summary(), note="timed region shorter than the 200 ms sampling period: sampled while "
+                                                  "the same steps kept running right after it")
     ms_own = ev[0].elapsed_time(end)
     ms_compute = ev[0].elapsed_time(ev[-1])  # this rank's own kernels, before it waits for the other ranks' blocks
-    launches = L.drm_launch_count() - launches0
     t = torch.tensor([ms_own, ms_compute], dtype=torch.float64, device=dev)
     all_ms = [t.clone() for _ in range(world)]
     if world > 1:
@@ -471,7 +483,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": W["h2d"], "d2h_bytes_per_step": W["d2h"],
                     "steps": len(e2e_times), "statistic": "median"},
             "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "clocks": clock_info,
         }
         if not args.no_cpu_baseline and W.get("cpu"):
             v, _, cores, sample = W["cpu"]()

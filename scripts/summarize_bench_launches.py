@@ -18,7 +18,7 @@ start, end = tabs[ngroups], tabs[2 * ngroups] if len(tabs) > 2 * ngroups else 10
 lines, tot, by = [], 0.0, {}
 group = -1
 for k in ids:
-    if not (start <= k[0] < end) or "drm::" not in k[1]:
+    if not (start <= k[0] < end) or not any(t in k[1] for t in ("drm::", "tree_", "pyr_", "render_")):
         continue
     m = cur[k]
     t = m.get("gpu__time_duration.sum", 0) / 1e6
