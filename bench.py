@@ -59,6 +59,9 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+JSON_OUT = sys.stdout  # main() replaces it by a private copy of fd 1
+
+
 def ncu_summary(workload):
     """Instruction-rate view of the dominant kernel from the committed ncu capture of this workload (profiles/)."""
     p = ROOT / "profiles" / "r2_issue.json"
@@ -346,7 +349,7 @@ def run_reference(args):
         "config": {"workload": f"{args.workload} (bounded sample per step on the host cores)", "footprint": args.footprint},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=JSON_OUT, flush=True)
 
 
 def main():
@@ -361,6 +364,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the JSON line and nothing else: whatever libraries print there (NCCL's version banner at init)
+    # goes to stderr
+    global JSON_OUT
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -488,7 +496,7 @@ def main():
         if not args.no_cpu_baseline and W.get("cpu"):
             v, _, cores, sample = W["cpu"]()
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
