@@ -1422,7 +1422,7 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->hand_over = 0.5f;
     o->limb_nv = 0.0f;
     o->limb_boost = 2.f;
-    o->limb_x = 8.f;
+    o->limb_x = 4.f;
     o->flat_scale = 1.4f;
     o->footprint_per_render = nullptr;
     o->collect_stats = 0;
