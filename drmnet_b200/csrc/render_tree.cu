@@ -1410,7 +1410,7 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     if (!o) return;
     o->kappa = 0.1f;
     o->rcap = 0.06f;
-    o->rcap_simple = 0.025f;
+    o->rcap_simple = 0.035f;
     o->horizon = 0.03f;
     o->kappa_diffuse = 0.1f;
     o->horizon_diffuse = 0.03f;

@@ -13,7 +13,7 @@ from drmnet_b200.synth import synthetic_envmap
 g = np.load(ROOT / "tests/golden/render_cells_1000x2000.npz")
 He, We, res = int(g["He"]), int(g["We"]), int(g["res"])
 meta, vals, cells = g["meta"], g["values"], g["cells"]
-want_S = (4, 8, 16)
+want_S = (1, 2, 4, 8, 16)
 idx = [i for i in range(len(meta)) if int(meta[i][3]) in want_S]
 variants = [("warm-up", {}), ("default", {})]
 for a in sys.argv[1:]:
