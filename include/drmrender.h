@@ -95,6 +95,10 @@ typedef struct DrmRenderOptions {
     const int32_t* footprint_per_render;  /* device, [N]: footprint S of each render (1, 2, 4, 8, 16; <= 0: chosen from
                                its roughness); NULL: footprint_S applies to every render */
     int collect_stats;      /* debug: count, per lattice pass, the pyramid cells visited and accepted (status words 16..35) */
+    float horizon_inner;    /* the horizon width for blocks of normals whose n.v stays above horizon_inner_nv * alpha (and
+                               outside the rim zone): the lobe does not sit on the horizon there; scaled by
+                               (cell_128 / cell)^(1/4) for refmaps coarser than 128^2 and never below `horizon` */
+    float horizon_inner_nv;
 } DrmRenderOptions;
 
 void drm_render_default_options(DrmRenderOptions* opts);
