@@ -1432,6 +1432,6 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->horizon_inner_nv = 4.f;
     o->limb_sub = 0.f;
     o->limb_cells = 1.3f;
-    o->limb_hand = 1e30f;
+    o->limb_hand = 32.f;
     o->limb_ramp = 0.f;
 }
