@@ -83,7 +83,7 @@ struct TreeArgs {
     int pool_cap;          // chunks in pool_out
     PyrGeom gs, gd;
     int B, He, We, N, res, pk, p, channel_first, pixcov;
-    float cell, domega_k, kappa, rcap, rcap_simple, hz, hz_in, hz_nv, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub, limb_cells;
+    float cell, domega_k, kappa, rcap, rcap_simple, hz, hz_in, hz_nv, hz_fin, kappa_d, hz_d, hand, limb_nv, limb_boost, limb_x, limb_hand, limb_ramp, limb_sub, limb_cells;
     float glx[TREE_MAX_P + 1][16], glw[TREE_MAX_P + 1][16];  // Gauss-Legendre lattices 1, 2, 4, 8, 16
     int stats;                   // debug: count visits / accepted records per pass into status[16..]
     int diff_cov;                // diffuse pass: 1x1 lattice with the cell covariance (else the render's own lattice)
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
         const float thr_p = rc.thr[p] * (limb ? g.limb_boost : 1.f);
         const float hand_p = limb ? g.limb_hand : g.hand;
         // the horizon ramp matters most where the lobe itself sits on it: n.v within a few lobe widths of zero
-        const float hz_p = (limb || nv_min < g.hz_nv * sqrtf(rc.alpha2)) ? g.hz : g.hz_in;
+        const float hz_p = (limb || nv_min < g.hz_nv * sqrtf(rc.alpha2)) ? (p == pk && rc.full2 ? g.hz_fin : g.hz) : g.hz_in;
         const float xthr = g.limb_ramp * sqrtf(rc.alpha2);
         const float alpha2 = rc.alpha2, kappa2 = g.kappa * g.kappa;
         // wide cells need the second-order terms of G1(n.d) whatever the lobe: without them the cap is half as large
@@ -1316,7 +1316,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     g.B = B; g.He = He; g.We = We; g.res = res; g.pk = L.pk; g.channel_first = channel_first;
     g.cell = (float)(M_PI / res);
     g.domega_k = (float)((2.0 * M_PI / We) * (M_PI / He));
-    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.hz_in = fmaxf(o.horizon, o.horizon_inner * fminf(1.f, powf((float)(M_PI / 128.0) / g.cell, 0.25f))); g.hz_nv = o.horizon_inner_nv; g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub; g.limb_cells = o.limb_cells;
+    g.kappa = o.kappa; g.rcap = o.rcap; g.rcap_simple = o.rcap_simple; g.hz = o.horizon; g.hz_in = fmaxf(o.horizon, o.horizon_inner * fminf(1.f, powf((float)(M_PI / 128.0) / g.cell, 0.25f))); g.hz_nv = o.horizon_inner_nv; g.hz_fin = fmaxf(o.horizon, o.horizon_finest * fminf(1.f, powf((float)(M_PI / 128.0) / g.cell, 0.25f))); g.kappa_d = o.kappa_diffuse; g.hz_d = o.horizon_diffuse; g.hand = o.hand_over; g.limb_nv = o.limb_nv; g.limb_boost = o.limb_boost; g.limb_x = o.limb_x; g.limb_hand = o.limb_hand; g.limb_ramp = o.limb_ramp; g.limb_sub = o.limb_sub; g.limb_cells = o.limb_cells;
     for (int p = 0; p <= TREE_MAX_P; ++p) gauss_legendre_t(1 << p, g.glx[p], g.glw[p]);
     // the diffuse lobe: 1x1 lattice whose node carries the cell's covariance, or the render's own lattice when the cells
     // are too wide for that (coarse refmaps) or the covariance is switched off
@@ -1430,6 +1430,7 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->collect_stats = 0;
     o->horizon_inner = 0.06f;
     o->horizon_inner_nv = 4.f;
+    o->horizon_finest = 0.045f;
     o->limb_sub = 0.f;
     o->limb_cells = 1.3f;
     o->limb_hand = 32.f;

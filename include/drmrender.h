@@ -100,6 +100,9 @@ typedef struct DrmRenderOptions {
                                outside the rim zone): the lobe does not sit on the horizon there; scaled by
                                (cell_128 / cell)^(1/4) for refmaps coarser than 128^2 and never below `horizon` */
     float horizon_inner_nv;
+    float horizon_finest;   /* the horizon width near the limb on the render's own lattice (its nodes are the exact normals)
+                               for the lobes that carry the per-cell horizon clamp (alpha >= alpha_full2); same scaling
+                               with the cell size */
 } DrmRenderOptions;
 
 void drm_render_default_options(DrmRenderOptions* opts);
