@@ -87,3 +87,25 @@ def test_workspace_too_small_is_reported_before_any_device_work(lib):
     assert rc == _lib.DRM_EWORKSPACE
     rc = lib.drm_render_refmaps(p, 1, 64, 128, None, p, p, None, 1, 16, 17, 0.0, 1, p, p, 64, None)
     assert rc == _lib.DRM_EINVAL and b"footprint_S" in lib.drm_last_error()
+
+
+def test_render_options_struct_mirrors_the_header(lib):
+    """The ctypes mirror of DrmRenderOptions has the header's fields, in the header's order, with matching C types --
+    a mismatch would silently shift every constant after it -- and the shipped defaults are the documented ones."""
+    header = (ROOT / "include" / "drmrender.h").read_text()
+    body = header[header.index("typedef struct DrmRenderOptions {"):header.index("} DrmRenderOptions;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"^\s*(const\s+int32_t\s*\*|float|int)\s*(\w+)\s*;", body, flags=re.M)
+    assert len(fields) >= 20
+    ctype_of = {"float": ctypes.c_float, "int": ctypes.c_int}
+    mirror = _lib.RenderOptions._fields_
+    assert [n for _, n in fields] == [n for n, _ in mirror]
+    for (ctype, name), (_, py) in zip(fields, mirror):
+        assert py is ctype_of.get(ctype, ctypes.c_void_p), name
+    o = _lib.default_render_options()
+    want = dict(kappa=0.1, rcap=0.06, rcap_simple=0.035, horizon=0.03, horizon_inner=0.06, horizon_inner_nv=4.0,
+                horizon_finest=0.045, kappa_diffuse=0.1, horizon_diffuse=0.03, level_scale=0.6, alpha_full2=0.1,
+                hand_over=0.5, limb_x=4.0, limb_cells=1.3, limb_boost=2.0, limb_hand=32.0, limb_ramp=0.0)
+    for k, v in want.items():
+        assert getattr(o, k) == pytest.approx(v, rel=1e-6), k
+    assert not o.footprint_per_render and o.collect_stats == 0
