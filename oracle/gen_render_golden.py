@@ -6,6 +6,8 @@ The fp64 brute force takes minutes per sharp render at 2000x1000, so it runs onc
 
     python -m oracle.gen_render_golden 1000 2000        # headline size (hours of CPU)
     python -m oracle.gen_render_golden 250 500
+    python -m oracle.gen_render_golden 1000 2000 0 rim  # render_cells_rim_<He>x<We>.npz: the bands of cells next to the
+                                                        # rim (rows / columns 1-4 and 123-126), where the rim rules switch
 """
 from __future__ import annotations
 
@@ -68,12 +70,21 @@ def cells_for(S: int, He: int) -> np.ndarray:
     return ro.strided_cells(RES, stride)
 
 
+def rim_band_cells() -> np.ndarray:
+    """rows / columns 1-4 and 123-126 (the cells just inside the outermost ring), every 16th position along them"""
+    band = [1, 2, 3, 4, RES - 5, RES - 4, RES - 3, RES - 2]
+    along = list(range(0, RES, 16)) + [RES - 1]
+    cl = {(b, a) for b in band for a in along} | {(a, b) for b in band for a in along}
+    return np.array(sorted(cl), np.int32)
+
+
 def main():
     He, We = int(sys.argv[1]), int(sys.argv[2])
     threads = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    rim = len(sys.argv) > 4 and sys.argv[4] == "rim"
     if threads:
         ro.set_threads(threads)
-    out_path = ROOT / "tests" / "golden" / f"render_cells_{He}x{We}.npz"
+    out_path = ROOT / "tests" / "golden" / (f"render_cells_rim_{He}x{We}.npz" if rim else f"render_cells_{He}x{We}.npz")
     cs = cases(He)
     amin = default_alpha_min(He)
     envs = {}
@@ -82,7 +93,7 @@ def main():
     for n, c in enumerate(cs):
         if c["seed"] not in envs:
             envs = {c["seed"]: synthetic_envmap(He, We, seed=c["seed"])}
-        cl = cells_for(c["S"], He)
+        cl = rim_band_cells() if rim else cells_for(c["S"], He)
         v = ro.render_oracle_cells(envs[c["seed"]], c["z"], c["view"], RES, cl, S=c["S"], alpha_min=amin)
         pad = np.full((289, 3), np.nan)
         pad[:len(v)] = v
