@@ -983,7 +983,7 @@ __global__ void __launch_bounds__(TREE_THREADS, 2) tree_spec_pass_kernel(const T
 }
 
 // ---- diffuse lobe: one pass, writes `out`.  1x1 lattice whose node carries the covariance of the refmap cell (fourth
-// order in the cell size: cells up to ~0.06 rad), or the render's own lattice for coarser refmaps ------------------------
+// order in the cell size: cells up to 0.03 rad), or the render's own lattice for coarser refmaps ------------------------
 __global__ void __launch_bounds__(TREE_THREADS, 2) tree_diff_kernel(const TreeArgs g) {
     extern __shared__ __align__(16) unsigned char tree_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1320,7 +1320,7 @@ extern "C" int drm_render_refmaps_opts(const float* env, int B, int He, int We, 
     for (int p = 0; p <= TREE_MAX_P; ++p) gauss_legendre_t(1 << p, g.glx[p], g.glw[p]);
     // the diffuse lobe: 1x1 lattice whose node carries the cell's covariance, or the render's own lattice when the cells
     // are too wide for that (coarse refmaps) or the covariance is switched off
-    g.diff_cov = (o.pixel_covariance && g.cell <= 0.06f) ? 1 : 0;
+    g.diff_cov = (o.pixel_covariance && g.cell <= 0.03f) ? 1 : 0;  // error ~ cell^4: 2e-5 at res 128, 4e-4 at res 64
     g.stats = o.collect_stats;
 
     const int tb = 128;
@@ -1425,12 +1425,12 @@ extern "C" void drm_render_default_options(DrmRenderOptions* o) {
     o->limb_nv = 0.0f;
     o->limb_boost = 2.f;
     o->limb_x = 4.f;
-    o->flat_scale = 1.4f;
+    o->flat_scale = 2.0f;
     o->footprint_per_render = nullptr;
     o->collect_stats = 0;
     o->horizon_inner = 0.06f;
     o->horizon_inner_nv = 4.f;
-    o->horizon_finest = 0.045f;
+    o->horizon_finest = 0.0375f;
     o->limb_sub = 0.f;
     o->limb_cells = 1.3f;
     o->limb_hand = 32.f;

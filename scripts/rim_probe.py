@@ -10,7 +10,9 @@ from drmnet_b200 import _lib
 from drmnet_b200.renderer import render_batch
 from drmnet_b200.synth import synthetic_envmap
 
-g = np.load(ROOT / "tests/golden/render_cells_1000x2000.npz")
+GOLD = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("file=")]
+sys.argv = [a for a in sys.argv if not a.startswith("file=")]
+g = np.load(ROOT / "tests/golden" / (GOLD[0] if GOLD else "render_cells_1000x2000.npz"))
 He, We, res = int(g["He"]), int(g["We"]), int(g["res"])
 meta, vals, cells = g["meta"], g["values"], g["cells"]
 want_S = (1, 2, 4, 8, 16)

@@ -103,8 +103,8 @@ def test_render_options_struct_mirrors_the_header(lib):
     for (ctype, name), (_, py) in zip(fields, mirror):
         assert py is ctype_of.get(ctype, ctypes.c_void_p), name
     o = _lib.default_render_options()
-    want = dict(kappa=0.1, rcap=0.06, rcap_simple=0.035, horizon=0.03, horizon_inner=0.06, horizon_inner_nv=4.0,
-                horizon_finest=0.045, kappa_diffuse=0.1, horizon_diffuse=0.03, level_scale=0.6, alpha_full2=0.1,
+    want = dict(kappa=0.1, rcap=0.06, rcap_simple=0.035, horizon=0.03, flat_scale=2.0, horizon_inner=0.06, horizon_inner_nv=4.0,
+                horizon_finest=0.0375, kappa_diffuse=0.1, horizon_diffuse=0.03, level_scale=0.6, alpha_full2=0.1,
                 hand_over=0.5, limb_x=4.0, limb_cells=1.3, limb_boost=2.0, limb_hand=32.0, limb_ramp=0.0)
     for k, v in want.items():
         assert getattr(o, k) == pytest.approx(v, rel=1e-6), k

@@ -319,3 +319,25 @@ def test_dropin_aovs_and_sensor_override():
     assert (big[6:-6, 6:-6] - 1).abs().max() < 0.05  # white furnace, z0
     big2 = r.rendering(torch.tensor(Z0), BRDF_PARAM_NAMES, sensor={"film": {"height": 20, "width": 20}})[0]
     assert big2.shape == (20, 20, 3)
+
+
+Z_CASES["gloss15"] = [0.2, 0.7, 0.7, 0.9, 0.15, 0.8]
+Z_CASES["edge_s2_metal"] = [1.0, 0.9, 0.5, 0.2, 0.48, 0.5]  # cell / alpha just above 0.1 at res 128: widest 2x2 lobe
+
+
+@pytest.mark.parametrize("res,zname,vi", [(64, "rough_dielectric", 3), (64, "rough_dielectric", 2), (64, "mixed", 3),
+                                          (64, "gloss15", 2), (64, "z0_mirror", 3), (256, "glossy_metal", 3),
+                                          (256, "z0_mirror", 2), (256, "mixed", 3), (128, "edge_s2_metal", 3)])
+def test_other_refmap_resolutions_match_single_level(res, zname, vi):
+    """BASELINE config[4] sweeps refmaps of 64^2 .. 256^2: the footprint the device picks, all cells, against the
+    single-level kernel on a 1000x500 map.  Includes the cases scripts/res_probe.py found hardest: a diffuse lobe at 64^2
+    (the covariance rule of the 1x1 lattice grows with cell^4 and is switched off above 0.03 rad), and the widest lobe of
+    the 2x2 footprint seen from behind (8e-5; one limb cell off by 7e-3 of its own value)."""
+    from drmnet_b200.renderer import auto_footprint, default_alpha_min
+    env = synthetic_envmap(500, 1000, seed=1004, device=DEV)[None]
+    z, v = torch.tensor([Z_CASES[zname]]), torch.tensor([VIEWS[vi]])
+    S = auto_footprint(float(np.clip(Z_CASES[zname][4], 0, 1)), res, default_alpha_min(500))
+    tree = render_batch(env, z, v, res=res, footprint_S=None, channel_first=False, check_status=True)[0].cpu().numpy()
+    flat = render_batch(env, z, v, res=res, footprint_S=S, channel_first=False, flat=True)[0].cpu().numpy()
+    assert rel_l2(tree, flat) <= 1e-4, rel_l2(tree, flat)
+    assert _local(tree, flat) <= 1e-2, _local(tree, flat)

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
-def _check(path, max_cases=None):
+def _check(path, max_cases=None, tol_by_S=None, loc_tol=1e-3):
     from drmnet_b200.renderer import render_batch
     from drmnet_b200.synth import synthetic_envmap
     g = np.load(path)
@@ -46,8 +46,8 @@ def _check(path, max_cases=None):
         err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
         loc = float(np.abs(got - ref).max() / np.abs(ref).max())
         worst = max(worst, err)
-        tol = 4e-4 if S == 16 else 1e-4
-        if err > tol or loc > 1e-3:
+        tol = (tol_by_S or {}).get(S, 4e-4 if S == 16 else 1e-4)
+        if err > tol or loc > loc_tol:
             failures.append(f"env {seed} z{zi} view{vi} S={S}: rel-L2 {err:.2e} (tol {tol:.0e}) worst cell/peak {loc:.2e}")
     assert not failures, f"{len(failures)} of {n} renders out of tolerance (worst rel-L2 {worst:.2e}):\n" + "\n".join(failures)
     return n
@@ -56,6 +56,20 @@ def _check(path, max_cases=None):
 def test_headline_size_2000x1000_vs_fp64_oracle_cells():
     n = _check(GOLDEN / "render_cells_1000x2000.npz")
     assert n >= 160  # 5 envmaps x 8 BRDF vectors x 4 views
+
+
+def test_rim_bands_2000x1000_vs_fp64_oracle_cells():
+    """The cells just inside the outermost ring (rows / columns 1-4 and 123-126, every 16th position along them): where
+    the rim zone of the lattice passes ends and the horizon width switches -- the constants of DESIGN.md 5 were swept
+    against the strided cells above, these were computed afterwards (oracle/gen_render_golden.py ... rim).
+
+    This subset holds ONLY the hardest cells of a refmap (the lobe sits on the horizon of the normal), so its relative L2 is
+    2-7 times the whole-image figure: measured 5.4e-5 (1x1), 1.3e-4 (2x2), 1.6e-4 (4x4), 2.1e-4 (8x8), 6.9e-4 (16x16),
+    worst cell 2.1e-3 of the image peak -- the same with the constants before the sweep except for the 1x1 footprint
+    (2.7e-5).  The bounds below pin that level."""
+    n = _check(GOLDEN / "render_cells_rim_1000x2000.npz", tol_by_S={1: 1e-4, 2: 1.7e-4, 4: 2.2e-4, 8: 2.7e-4, 16: 9e-4},
+               loc_tol=2.7e-3)
+    assert n >= 160
 
 
 def test_500x250_vs_fp64_oracle_cells():
