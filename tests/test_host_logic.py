@@ -142,3 +142,24 @@ def test_img2refmap_batches_split_at_the_per_call_pixel_limit():
     assert split_batch([0, 0, 0], 5) == [(0, 2)]
     with pytest.raises(ValueError):
         split_batch([0, 7], 5)
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): stdout is exactly one JSON line carrying
+    the metric of the workload, `impl`, a `cpu_baseline` describing the run and an `e2e` object without copies."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    p = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--workload", "img2refmap",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "img2refmaps/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
